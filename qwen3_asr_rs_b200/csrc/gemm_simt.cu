@@ -1,0 +1,74 @@
+// gemm_simt.cu -- fp32 CUDA-core GEMM with the shared A-loaders / epilogues.
+// Role: (1) on-device reference for the tcgen05 GEMM (same inputs, same epilogues),
+// (2) the path for shapes the tensor-core kernel does not cover.  64x64x16 tiles, 256 threads,
+// 4x4 register blocking, fp32 accumulate of exact bf16*bf16 products.
+#include "internal.h"
+#include "epilogue.cuh"
+
+namespace asrb {
+
+static constexpr int BM = 64, BN = 64, BK = 16;
+
+__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmA A, const bf16* __restrict__ W, int N, GemmEpi E) {
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Ws[BK][BN + 4];
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;   // 16 x 16 threads, each 4(m) x 4(n)
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < A.K; k0 += BK) {
+        // load tiles: 64x16 elements each, 256 threads x 4
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int idx = tid + i * 256;
+            int r = idx >> 4, kk = idx & 15;
+            int m = m0 + r, k = k0 + kk;
+            As[kk][r] = (m < A.M && k < A.K) ? load_a(A, m, k) : 0.f;
+            int n = n0 + r;
+            Ws[kk][r] = (n < N && k < A.K) ? __bfloat162float(W[(size_t)n * A.K + k]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int m = m0 + ty * 4 + i;
+        if (m >= A.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+            int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            epi_store2(E, N, m, n, acc[i][j], acc[i][j + 1], n + 1 < N);
+        }
+    }
+}
+
+void launch_gemm_simt(const GemmA& A, const bf16* W, int N, const GemmEpi& E, cudaStream_t st) {
+    dim3 grid((N + BN - 1) / BN, (A.M + BM - 1) / BM);
+    if (A.M <= 0 || N <= 0) return;
+    gemm_simt_kernel<<<grid, 256, 0, st>>>(A, W, N, E);
+    ASRB_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_gemm(const GemmA& A, const bf16* W, int N, const GemmEpi& E, int impl, cudaStream_t st) {
+    if (impl == GEMM_TC && launch_gemm_tc(A, W, N, E, st)) return;
+    launch_gemm_simt(A, W, N, E, st);
+}
+
+}  // namespace asrb

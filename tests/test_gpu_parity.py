@@ -1,0 +1,193 @@
+"""GPU: the CUDA hot path (through the C ABI) vs the CPU oracle on identical seeded inputs.
+
+Tolerances (floating point; the oracle is fp32 and itself only reproducible to
+summation-order noise, e.g. 1.7e-5 between two FFT implementations of the mel --
+oracle/pin_against_hf.py):
+  mel        max |d| <= 2e-4   (values in [-0.7, 1.4])
+  encoder    max |d| <= 1e-3 * max|ref|
+  logits     max |d| <= 2e-3 * max|ref|
+  token ids  exact equality with the oracle's greedy output
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from qwen3_asr_rs_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+MEL_TOL, ENC_RTOL, LOGIT_RTOL = 2e-4, 1e-3, 2e-3
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("seconds", [0.02, 0.5, 1.003, 3.07, 11.55, 30.0])
+def test_mel_parity(tiny_engine, report, seconds):
+    x = synth.make_clip(11, seconds)
+    got = tiny_engine.mel([x])[0]
+    ref = O.extract_mel(x).numpy()
+    assert got.shape == ref.shape
+    err = float(np.abs(got - ref).max())
+    report[f"mel_abs_err_{seconds}s"] = err
+    assert err <= MEL_TOL
+
+
+def test_mel_batch_ragged(tiny_engine, report):
+    clips = [synth.make_clip(20 + i, s) for i, s in enumerate([2.0, 0.31, 7.77, 1.0])]
+    got = tiny_engine.mel(clips)
+    for g, c in zip(got, clips):
+        ref = O.extract_mel(c).numpy()
+        assert g.shape == ref.shape and np.abs(g - ref).max() <= MEL_TOL
+
+
+def test_mel_pure_noise_and_silence(tiny_engine):
+    rng = np.random.default_rng(0)
+    noise = (rng.standard_normal(16000) * 0.1).astype(np.float32)
+    silence = np.zeros(8000, np.float32)
+    got = tiny_engine.mel([noise, silence])
+    assert np.abs(got[0] - O.extract_mel(noise).numpy()).max() <= MEL_TOL
+    assert np.abs(got[1] - O.extract_mel(silence).numpy()).max() <= MEL_TOL
+
+
+@pytest.mark.parametrize("seconds", [0.6, 1.0, 5.0, 8.0, 8.5, 11.55, 30.0])
+def test_encoder_parity(tiny, tiny_engine, report, seconds):
+    """covers: single chunk, tail chunks of assorted lengths, C <= 8 (mask None), C > 8 (windows)."""
+    _, _, model = tiny
+    x = synth.make_clip(31, seconds)
+    tiny_engine.mel([x])
+    got = tiny_engine.encode()[0]
+    ref = model.encode(O.extract_mel(x)).numpy()
+    assert got.shape == ref.shape
+    r = _rel(got, ref)
+    report[f"enc_rel_err_{seconds}s"] = r
+    assert r <= ENC_RTOL
+
+
+@pytest.mark.parametrize("tail_frames", [1, 2, 7, 8, 9, 16, 17, 33, 50, 64, 65, 99])
+def test_encoder_tail_chunk_lengths(tiny, tiny_engine, tail_frames):
+    _, _, model = tiny
+    n = (100 + tail_frames) * 160 - 37            # ragged sample count inside the last frame
+    x = synth.make_clip(40 + tail_frames, n / 16000.0)[:n]
+    tiny_engine.mel([x])
+    got = tiny_engine.encode()[0]
+    ref = model.encode(O.extract_mel(x)).numpy()
+    assert got.shape == ref.shape == (13 + O.feat_extract_output_length(tail_frames), 256)
+    assert _rel(got, ref) <= ENC_RTOL
+
+
+def test_encoder_batch_mixed_windows(tiny, tiny_engine):
+    _, _, model = tiny
+    clips = [synth.make_clip(50 + i, s) for i, s in enumerate([3.3, 12.0, 0.9, 17.5])]
+    tiny_engine.mel(clips)
+    got = tiny_engine.encode()
+    for g, c in zip(got, clips):
+        ref = model.encode(O.extract_mel(c)).numpy()
+        assert g.shape == ref.shape and _rel(g, ref) <= ENC_RTOL
+
+
+def test_prefill_and_step_logits(tiny, tiny_engine, report):
+    _, _, model = tiny
+    x = synth.make_clip(60, 6.2)
+    ref = O.transcribe_ids(model, x, max_new_tokens=6, keep_logits=True)
+    tiny_engine.mel([x])
+    tiny_engine.encode()
+    seq, logits = tiny_engine.prefill()
+    assert seq[0] == ref.audio_embeds.shape[0] + 15
+    r0 = _rel(logits[0], ref.prefill_logits.numpy())
+    report["prefill_logits_rel_err"] = r0
+    assert r0 <= LOGIT_RTOL
+    for i in range(5):
+        nxt, lg = tiny_engine.decode_step()
+        assert nxt[0] == ref.ids[i]
+        r = _rel(lg[0], ref.step_logits[i].numpy())
+        report[f"step{i}_logits_rel_err"] = r
+        assert r <= LOGIT_RTOL
+
+
+@pytest.mark.parametrize("decode", ["phases", "mega"])
+def test_token_ids_exact_tiny(tiny, tiny_engine, report, decode):
+    _, _, model = tiny
+    tiny_engine.set_option("decode", decode)
+    try:
+        for idx, sec, n_new in [(70, 4.0, 48), (71, 12.3, 32), (72, 0.8, 40)]:
+            x = synth.make_clip(idx, sec)
+            ref = O.transcribe_ids(model, x, max_new_tokens=n_new, keep_logits=True)
+            got = tiny_engine.transcribe_ids([x], max_new_tokens=n_new)
+            margins = [float(l.topk(2).values[0] - l.topk(2).values[1]) for l in [ref.prefill_logits] + ref.step_logits[:-1]]
+            report[f"ids_{decode}_{idx}_min_margin"] = min(margins)
+            assert got.ids[0] == ref.ids, (decode, idx, min(margins))
+    finally:
+        tiny_engine.set_option("decode", "mega")
+
+
+def test_token_ids_batch_and_forced_language(tiny, tiny_engine):
+    _, _, model = tiny
+    clips = [synth.make_clip(80 + i, s) for i, s in enumerate([2.5, 9.1, 5.0])]
+    lang = [None, [11528, 6364], [11528, 8453, 55]]     # arbitrary in-vocab ids standing in for "language Xxx"
+    got = tiny_engine.transcribe_ids(clips, language_ids=lang, max_new_tokens=20)
+    for g, c, l in zip(got.ids, clips, lang):
+        ref = O.transcribe_ids(model, c, language_ids=l, max_new_tokens=20)
+        assert g == ref.ids
+
+
+def test_eos_stops_generation(tiny):
+    """EOS semantics (inference.rs:161-166): a model whose argmax is EOS right after prefill
+    generates nothing; built by making the EOS embedding row dominate the tied lm_head."""
+    import torch
+    from qwen3_asr_rs_b200 import AsrInference, config_tiny
+    cfg, w, _ = tiny
+    w2 = dict(w)
+    e = w["thinker.model.embed_tokens.weight"].float().clone()
+    x = synth.make_clip(90, 1.5)
+    base = O.OracleModel(cfg, w2)
+    r = O.transcribe_ids(base, x, max_new_tokens=3)
+    # make token r.ids[1]'s successor EOS: copy a scaled version of the 2nd generated token's row direction
+    e[151645] = e[r.ids[2]] * 1.5
+    w2["thinker.model.embed_tokens.weight"] = e.bfloat16()
+    model = O.OracleModel(cfg, w2)
+    ref = O.transcribe_ids(model, x, max_new_tokens=12)
+    eng = AsrInference.from_weights(config_tiny(), w2, device=0)
+    try:
+        got = eng.transcribe_ids([x], max_new_tokens=12)
+    finally:
+        eng.close()
+    assert got.ids[0] == ref.ids
+    assert len(ref.ids) < 12          # EOS actually hit
+
+
+def test_errors_are_statuses(tiny_engine):
+    from qwen3_asr_rs_b200._lib import AsrbError
+    with pytest.raises(AsrbError):
+        tiny_engine.mel([np.zeros(100, np.float32)])           # too short for reflect padding
+
+
+def test_full_size_0p6b_one_clip(report):
+    """Qwen3-ASR-0.6B dims, one 30 s clip (BASELINE.json configs[1] shape), synthetic weights:
+    exact ids + logits tolerance against the oracle run on the host cores."""
+    from qwen3_asr_rs_b200 import AsrInference, config_0p6b
+    cfg = O.cfg_0p6b()
+    w = synth.make_weights(cfg, 1)
+    x = synth.make_clip(0, 30.0)
+    n_new = 24
+    ref = O.transcribe_ids(O.OracleModel(cfg, w), x, max_new_tokens=n_new, keep_logits=True, lm_head_all_rows=False)
+    eng = AsrInference.from_weights(config_0p6b(), w, device=0)
+    try:
+        mel = eng.mel([x])[0]
+        report["full_mel_abs_err"] = float(np.abs(mel - ref.mel.numpy()).max())
+        enc = eng.encode()[0]
+        report["full_enc_rel_err"] = _rel(enc, ref.audio_embeds.numpy())
+        seq, logits = eng.prefill()
+        report["full_prefill_logits_rel_err"] = _rel(logits[0], ref.prefill_logits.numpy())
+        assert seq[0] == 405 and enc.shape == (390, 1024)
+        got = eng.transcribe_ids([x], max_new_tokens=n_new)
+        margins = [float(l.topk(2).values[0] - l.topk(2).values[1]) for l in [ref.prefill_logits] + ref.step_logits[:-1]]
+        report["full_min_margin"] = min(margins)
+        report["full_stage_ms"] = got.stage_ms
+        assert report["full_mel_abs_err"] <= MEL_TOL
+        assert report["full_enc_rel_err"] <= ENC_RTOL
+        assert report["full_prefill_logits_rel_err"] <= LOGIT_RTOL
+        assert got.ids[0] == ref.ids
+    finally:
+        eng.close()
