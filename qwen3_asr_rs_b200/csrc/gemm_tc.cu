@@ -1,4 +1,295 @@
+// gemm_tc.cu -- tcgen05 tensor-core GEMM for the encoder / prefill contractions.
+//
+//   D[m][n] = sum_p sum_k A_p(m,k) * W[n][k]        p = bf16 split planes of the fp32 activation
+//
+// Replaces every Linear::forward (layers.rs:74-80) with M > 1 and conv2d2/conv2d3 (audio_encoder.rs:
+// 128-129) as implicit GEMM.  B200-native structure: one 128x128 output tile per CTA, operands
+// staged by TMA (cp.async.bulk.tensor, 128B swizzle) into a 3-stage shared-memory ring, a single
+// elected thread issues tcgen05.mma (kind::f16, M=128 N=128 K=16) accumulating in TMEM (fp32),
+// tcgen05.commit releases ring slots / signals the epilogue, four epilogue warps read the
+// accumulator with tcgen05.ld and apply the fused epilogues of epilogue.cuh.
+//
+// Precision: weights are exact bf16; each fp32 activation is stored as 3 bf16 planes
+// (hi + mid + lo == x to 1 ulp, common.cuh).  bf16 x bf16 products are exact in fp32 and the
+// accumulator is fp32, so the result matches an fp32 GEMM to accumulation-order noise -- that is
+// what keeps greedy token ids identical to the fp32 oracle.  planes = 1 gives the plain bf16 GEMM.
+//
+// The conv A-operand is never materialised (no im2col): the activation lives in a parity-split
+// channels-last layout so that each of the 9 filter taps is a plain (unit-stride) TMA box of a
+// 5-D tensor map; out-of-bounds coordinates (the conv padding) are zero-filled by TMA.
+#include <cuda.h>
+#include <map>
+#include <tuple>
 #include "internal.h"
+#include "epilogue.cuh"
+
 namespace asrb {
-bool launch_gemm_tc(const GemmA&, const bf16*, int, const GemmEpi&, cudaStream_t) { return false; }
+namespace tc {
+
+static constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+static constexpr int TILE_A_BYTES = BM * BK * 2;      // 16 KB per plane
+static constexpr int TILE_B_BYTES = BN * BK * 2;      // 16 KB
+static constexpr int STAGE_BYTES = 3 * TILE_A_BYTES + TILE_B_BYTES;   // 64 KB
+static constexpr int NTHREADS = 192;                  // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+static constexpr int TMEM_COLS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar)) : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 64 bf16 (128 B), 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffff) >> 4);          // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=128, M=128
+__device__ __forceinline__ uint32_t make_idesc() {
+    uint32_t d = 0;
+    d |= 1u << 4;                  // c_format = F32
+    d |= 1u << 7;                  // a_format = BF16
+    d |= 1u << 10;                 // b_format = BF16
+    d |= (uint32_t)(BN >> 3) << 17;
+    d |= (uint32_t)(BM >> 4) << 24;
+    return d;
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct ConvGeom { int OH, OW, box_h, tiles_per_chunk, kblk_per_tap, a_box_bytes; };
+
+// A_MODE 0: plain [planes][M][K];  1: conv taps over the parity layout
+template <int A_MODE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               int M, int N, int K, int nplanes, ConvGeom cg, GemmEpi E) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    const int num_kb = K / BK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    }
+    if (warp == 1) {   // TMEM allocation is warp-collective
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile coordinates
+    int m0 = blockIdx.y * BM;              // plain
+    int chunk = 0, oh0 = 0;                // conv
+    if (A_MODE == 1) { chunk = blockIdx.y / cg.tiles_per_chunk; oh0 = (blockIdx.y % cg.tiles_per_chunk) * cg.box_h; }
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        // TMA always delivers (and counts) the full box, zero-filling out-of-bounds elements; the conv box
+        // has OW*box_h (<= 128) rows, the remaining rows of the UMMA tile are never read back.
+        const uint32_t a_bytes = (A_MODE == 0) ? (uint32_t)TILE_A_BYTES : (uint32_t)cg.a_box_bytes;
+        const uint32_t stage_tx = (uint32_t)nplanes * a_bytes + (uint32_t)TILE_B_BYTES;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES; const uint32_t par = (kb / STAGES) & 1;
+            mbar_wait(&empty[s], par ^ 1);
+            uint8_t* st = smem + s * STAGE_BYTES;
+            mbar_expect_tx(&full[s], stage_tx);
+            if (A_MODE == 0) {
+                for (int p = 0; p < nplanes; ++p) tma_load_3d(st + p * TILE_A_BYTES, &mapA, kb * BK, m0, p, &full[s]);
+            } else {
+                const int tap = kb / cg.kblk_per_tap, cb = kb % cg.kblk_per_tap;
+                const int kh = tap / 3, kw = tap % 3;
+                const int ph = (kh == 1) ? 0 : 1, pw = (kw == 1) ? 0 : 1;
+                const int h = oh0 + (kh == 0 ? -1 : 0), w = (kw == 0 ? -1 : 0);
+                for (int p = 0; p < nplanes; ++p)
+                    tma_load_5d(st + p * TILE_A_BYTES, &mapA, cb * BK, w, h, (chunk * 2 + ph) * 2 + pw, p, &full[s]);
+            }
+            tma_load_2d(st + 3 * TILE_A_BYTES, &mapB, kb * BK, n0, &full[s]);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = make_idesc();
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES; const uint32_t par = (kb / STAGES) & 1;
+            mbar_wait(&full[s], par);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+            const uint64_t bdesc = make_smem_desc(sa + 3 * TILE_A_BYTES);
+            for (int p = 0; p < nplanes; ++p) {
+                const uint64_t adesc = make_smem_desc(sa + p * TILE_A_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)     // +32 B per K=16 step inside the 128 B swizzle atom
+                    umma(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | p | k) != 0);
+            }
+            umma_commit(&empty[s]);                   // slot reusable once these MMAs retire
+        }
+        umma_commit(acc_full);
+    } else if (warp >= 2) {
+        // ================= epilogue =================
+        mbar_wait(acc_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+        const int r = quad * 32 + lane;               // row inside the tile
+        long long m = -1;
+        if (A_MODE == 0) { if (m0 + r < M) m = m0 + r; }
+        else {
+            const int oh = oh0 + r / cg.OW, ow = r % cg.OW;
+            if (r < cg.box_h * cg.OW && oh < cg.OH) m = ((long long)chunk * cg.OH + oh) * cg.OW + ow;
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+            if (m >= 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const int n = n0 + c0 + j;
+                    if (n < N) epi_store2(E, N, (int)m, n, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), n + 1 < N);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host: tensor maps ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        ASRB_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+        ASRB_REQUIRE(p != nullptr && qr == cudaDriverEntryPointSuccess, ASRB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+static CUtensorMap make_map(const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    CUtensorMap m;
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error(ASRB_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return m;
+}
+
+static size_t smem_bytes() { return (size_t)STAGES * STAGE_BYTES + 1024 + 256; }
+
+}  // namespace tc
+
+bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& E, cudaStream_t st) {
+    using namespace tc;
+    if (A.K % BK != 0 || A.M <= 0 || N <= 0) return false;
+    if (A.nplanes < 1 || A.nplanes > 3) return false;
+    if ((reinterpret_cast<uintptr_t>(A.a) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) return false;
+    // B: [N][K] row-major bf16
+    cuuint64_t bd[2] = {(cuuint64_t)A.K, (cuuint64_t)N};
+    cuuint64_t bs[1] = {(cuuint64_t)A.K * 2};
+    cuuint32_t bb[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    CUtensorMap mapB = make_map(W, 2, bd, bs, bb);
+    ConvGeom cg{};
+    const size_t smem = smem_bytes();
+    if (A.mode == A_PLAIN) {
+        if (A.plane_stride % 8 != 0 && A.nplanes > 1) return false;
+        cuuint64_t ad[3] = {(cuuint64_t)A.K, (cuuint64_t)A.M, (cuuint64_t)3};
+        cuuint64_t as[2] = {(cuuint64_t)A.lda * 2, (cuuint64_t)A.plane_stride * 2};
+        cuuint32_t ab[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1};
+        CUtensorMap mapA = make_map(A.a, 3, ad, as, ab);
+        static bool attr = false;
+        if (!attr) { ASRB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        dim3 grid((N + BN - 1) / BN, (A.M + BM - 1) / BM);
+        gemm_tc_kernel<0><<<grid, NTHREADS, smem, st>>>(mapA, mapB, A.M, N, A.K, A.nplanes, cg, E);
+    } else {
+        if (A.cpad % BK != 0 || A.OW > BM) return false;
+        const int per = A.OH * A.OW;
+        const int chunks = A.M / per;
+        cg.OH = A.OH; cg.OW = A.OW; cg.box_h = std::min(A.OH, BM / A.OW);
+        cg.tiles_per_chunk = (A.OH + cg.box_h - 1) / cg.box_h; cg.kblk_per_tap = A.cpad / BK;
+        cg.a_box_bytes = A.OW * cg.box_h * BK * 2;
+        // [plane][chunk*4 + ph*2 + pw][Hh][Wh][cpad]
+        cuuint64_t ad[5] = {(cuuint64_t)A.cpad, (cuuint64_t)A.Wh, (cuuint64_t)A.Hh, (cuuint64_t)chunks * 4, 3};
+        cuuint64_t as[4] = {(cuuint64_t)A.cpad * 2, (cuuint64_t)A.Wh * A.cpad * 2, (cuuint64_t)A.Hh * A.Wh * A.cpad * 2,
+                            (cuuint64_t)A.plane_stride * 2};
+        cuuint32_t ab[5] = {(cuuint32_t)BK, (cuuint32_t)A.OW, (cuuint32_t)cg.box_h, 1, 1};
+        CUtensorMap mapA = make_map(A.a, 5, ad, as, ab);
+        static bool attr = false;
+        if (!attr) { ASRB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        dim3 grid((N + BN - 1) / BN, chunks * cg.tiles_per_chunk);
+        gemm_tc_kernel<1><<<grid, NTHREADS, smem, st>>>(mapA, mapB, A.M, N, A.K, A.nplanes, cg, E);
+    }
+    ASRB_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+}  // namespace asrb

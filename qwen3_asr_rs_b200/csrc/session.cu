@@ -58,6 +58,7 @@ struct Session {
     float last_ms[6] = {0, 0, 0, 0, 0, 0};
     bool resident = false, timing = false;
     int64_t launches = 0, decode_steps = 0;
+    int greedy_done = 0;   // greedy applications since prefill (tokens appended or EOS), bounds max_new
     ~Session();
 };
 
@@ -401,6 +402,9 @@ void session_prefill(Session* s, const int64_t* const* lang_ids, const int32_t* 
     // final norm + lm_head on the last row of each utterance only (the reference computes all S rows,
     // text_decoder.rs:111-112, and uses row S-1, inference.rs:156)
     launch_lmhead_argmax(m, s->hid, s->d_lastrow, B, s->db, last_logits != nullptr, st, &s->launches);
+    // greedy bookkeeping for token 0 (inference.rs:161-170): argmax, EOS check, append, embed
+    launch_greedy(m, s->db, B, st, &s->launches);
+    s->greedy_done = 1;
     if (seq_lens_out) for (int b = 0; b < B; ++b) seq_lens_out[b] = s->S[b];
     if (last_logits) {
         ASRB_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -417,24 +421,31 @@ void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* 
                              size_t cache_layer_stride, size_t cache_seq_stride, int max_ctx, cudaStream_t st,
                              int64_t* launches);
 
+// one iteration of the loop body: decoder forward on the pending token, then the greedy bookkeeping
+// that selects / appends / embeds the next one.  (The fused kernel does both.)
+static bool use_mega(Session* s, bool write_logits) {
+    return s->decode_mode == 1 && !write_logits && decode_mega_supported(*s->m, s->B);
+}
 static void forward_step(Session* s, bool write_logits) {
     Model& m = *s->m;
-    if (s->decode_mode == 1 && !write_logits && decode_mega_supported(m, s->B))
+    if (use_mega(s, write_logits)) {
         launch_decode_step_mega(m, s->db, s->B, s->kcache, s->vcache, s->cache_layer_stride, s->cache_seq_stride, s->max_ctx,
                                 s->st, &s->launches);
-    else
+    } else {
         launch_decode_step_phases(m, s->db, s->B, s->kcache, s->vcache, s->cache_layer_stride, s->cache_seq_stride, s->max_ctx,
                                   write_logits, s->st, &s->launches);
+        launch_greedy(m, s->db, s->B, s->st, &s->launches);
+    }
 }
 
 void session_decode_step(Session* s, int64_t* next_ids_out, float* logits) {
     ASRB_REQUIRE(s->stage >= 3, ASRB_ERR_STATE, "decode_step called before prefill");
     Model& m = *s->m; const int B = s->B;
     ASRB_CUDA_CHECK(cudaSetDevice(m.ctx->device));
-    launch_greedy(m, s->db, B, s->st, &s->launches);
-    forward_step(s, logits != nullptr);
-    s->decode_steps += 1;
+    // the id selected by the previous greedy application is the one this iteration consumes
     ASRB_CUDA_CHECK(cudaMemcpyAsync(s->h_next, s->db.next_id, B * sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    forward_step(s, logits != nullptr);
+    s->decode_steps += 1; s->greedy_done += 1;
     ASRB_CUDA_CHECK(cudaStreamSynchronize(s->st));
     if (next_ids_out) for (int b = 0; b < B; ++b) next_ids_out[b] = s->h_next[b];
     if (logits) ASRB_CUDA_CHECK(cudaMemcpy(logits, s->db.logits, (size_t)B * m.d.c.vocab_size * sizeof(float), cudaMemcpyDeviceToHost));
@@ -445,38 +456,34 @@ void session_generate(Session* s, int max_new_tokens, int32_t* ids_out, int32_t*
     ASRB_REQUIRE(max_new_tokens >= 1 && max_new_tokens <= s->max_new, ASRB_ERR_INVALID, "max_new_tokens exceeds session capacity");
     Model& m = *s->m; const int B = s->B; cudaStream_t st = s->st;
     ASRB_CUDA_CHECK(cudaSetDevice(m.ctx->device));
-    // one iteration = greedy bookkeeping (argmax of pending logits, EOS, append, embed) + forward.
-    // The reference runs `forward` after the last appended token too and discards its logits
+    // Token 0 was selected at the end of prefill; each further token costs one forward + greedy.  The
+    // reference also runs `forward` after the last appended token and discards its logits
     // (inference.rs:160-200); that wasted forward is not issued here.
-    const bool use_graph = true;
-    const int mode_key = s->decode_mode * 16 + B;
-    if (use_graph && (s->step_graph == nullptr || s->graph_mode != mode_key)) {
-        if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = nullptr; }
-        // warm (sets func attributes outside capture), then capture one iteration
-        cudaGraph_t g = nullptr;
-        int64_t dummy = 0;
-        ASRB_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        try {
+    const int steps = std::max(0, max_new_tokens - s->greedy_done);
+    const bool mega = use_mega(s, false);
+    if (!mega) {   // per-phase path: ~142 launches per step -> replay them as one CUDA graph
+        const int mode_key = s->decode_mode * 16 + B;
+        if (s->step_graph == nullptr || s->graph_mode != mode_key) {
+            if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = nullptr; }
+            cudaGraph_t g = nullptr;
             int64_t before = s->launches;
-            launch_greedy(m, s->db, B, st, &s->launches);
-            forward_step(s, false);
-            dummy = s->launches - before;
+            ASRB_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            try { forward_step(s, false); }
+            catch (...) { cudaStreamEndCapture(st, &g); if (g) cudaGraphDestroy(g); s->launches = before; throw; }
+            ASRB_CUDA_CHECK(cudaStreamEndCapture(st, &g));
+            ASRB_CUDA_CHECK(cudaGraphInstantiate(&s->step_graph, g, 0));
+            cudaGraphDestroy(g);
+            s->graph_mode = mode_key; s->graph_B = (int)(s->launches - before);   // kernels per replay
             s->launches = before;
-        } catch (...) { cudaStreamEndCapture(st, &g); if (g) cudaGraphDestroy(g); throw; }
-        ASRB_CUDA_CHECK(cudaStreamEndCapture(st, &g));
-        ASRB_CUDA_CHECK(cudaGraphInstantiate(&s->step_graph, g, 0));
-        cudaGraphDestroy(g);
-        s->graph_mode = mode_key; s->graph_B = (int)dummy;   // kernels per graph launch
+        }
     }
-    int already = 0;   // tokens appended so far by decode_step calls are accounted on device (n_out)
-    (void)already;
     const int check_every = 16;
     bool all_done = false;
-    for (int it = 0; it < max_new_tokens && !all_done; ++it) {
-        if (it == max_new_tokens - 1) { launch_greedy(m, s->db, B, st, &s->launches); break; }
-        ASRB_CUDA_CHECK(cudaGraphLaunch(s->step_graph, st));
-        s->launches += s->graph_B; s->decode_steps += 1;
-        if ((it + 1) % check_every == 0) {
+    for (int it = 0; it < steps && !all_done; ++it) {
+        if (mega) forward_step(s, false);
+        else { ASRB_CUDA_CHECK(cudaGraphLaunch(s->step_graph, st)); s->launches += s->graph_B; }
+        s->decode_steps += 1; s->greedy_done += 1;
+        if ((it + 1) % check_every == 0 && it + 1 < steps) {
             ASRB_CUDA_CHECK(cudaMemcpyAsync(s->h_done, s->db.done, B * sizeof(int), cudaMemcpyDeviceToHost, st));
             ASRB_CUDA_CHECK(cudaStreamSynchronize(st));
             all_done = true;
