@@ -25,9 +25,10 @@ static constexpr int NCONS_WARPS = 8;
 static constexpr int NCONS = NCONS_WARPS * 32;          // 256 consumer threads
 static constexpr int NTHREADS = NCONS + 32;             // + 1 producer warp
 static constexpr int SLOT_BYTES = 24 * 1024;
-static constexpr int NSLOT = 8;
+static constexpr int NSLOT = 5;                         // weight ring: 120 KB in flight per SM
+static constexpr int KV_KEYS = 64;                      // keys per attention split (K and V tiles staged in smem)
+static constexpr int KV_TILE_BYTES = KV_KEYS * 128 * 4; // 32 KB each for K and V (fp32 cache)
 static constexpr int XS_FLOATS = 3072 + 64;             // activation vector / attention scratch
-static constexpr int MAX_SPLIT_KEYS = 1024;
 
 struct Params {
     const DecLayerW* layers;     // device array [L]
@@ -228,10 +229,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     extern __shared__ __align__(1024) uint8_t smem[];
     Ring ring;
     ring.slots = smem;
-    float* xs = reinterpret_cast<float*>(smem + (size_t)NSLOT * SLOT_BYTES);
+    uint8_t* kv_smem = smem + (size_t)NSLOT * SLOT_BYTES;              // [K tile | V tile]
+    float* xs = reinterpret_cast<float*>(kv_smem + 2 * KV_TILE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(xs + XS_FLOATS);
     ring.full = bars; ring.empty = bars + NSLOT;
-    float* red = reinterpret_cast<float*>(bars + 2 * NSLOT);          // [64]
+    uint64_t* kv_full = bars + 2 * NSLOT; uint64_t* kv_empty = kv_full + 1;
+    float* red = reinterpret_cast<float*>(bars + 2 * NSLOT + 2);      // [64]
     int* ired = reinterpret_cast<int*>(red + 64);                      // [64]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_producer = warp == NCONS_WARPS;
@@ -240,16 +243,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
 
     if (tid == 0) {
         for (int i = 0; i < NSLOT; ++i) { mbar_init(&ring.full[i], 1); mbar_init(&ring.empty[i], NCONS_WARPS); }
+        mbar_init(kv_full, 1); mbar_init(kv_empty, NCONS_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
+    // attention work item of this CTA: (kv head att_g, keys [att_j0, att_j0 + KV_KEYS)); keys < pos are
+    // already in the cache (n_old of them fall in this split), key `pos` is produced in this step.
+    const int pos = __ldcg(p.pos);
+    const bool att_cta = (int)blockIdx.x < p.nkv * p.nsplit;
+    const int att_g = blockIdx.x / p.nsplit, att_j0 = (blockIdx.x % p.nsplit) * KV_KEYS;
+    const int n_old = att_cta ? max(0, min(pos - att_j0, KV_KEYS)) : 0;
+    uint32_t kvq = 0;
     uint32_t q = 0;
     if (is_producer) {
         if (lane == 0) {
             for (int l = 0; l < p.L; ++l) {
                 const DecLayerW w = p.layers[l];
                 produce(make_slice(w.wqkv, QD + 2 * p.KVD, H, 1), ring, q);
+                if (n_old > 0) {   // K/V rows of earlier positions do not depend on this step: prefetch them too
+                    mbar_wait(kv_empty, (kvq & 1) ^ 1);
+                    const uint32_t bytes = (uint32_t)n_old * 128 * 4;
+                    mbar_expect_tx(kv_full, 2 * bytes);
+                    const size_t off = (size_t)l * p.cache_layer_stride + ((size_t)att_g * p.max_ctx + att_j0) * 128;
+                    bulk_g2s(kv_smem, p.kcache + off, bytes, kv_full);
+                    bulk_g2s(kv_smem + KV_TILE_BYTES, p.vcache + off, bytes, kv_full);
+                    ++kvq;
+                }
                 produce(make_slice(w.wo, H, QD, 1), ring, q);
                 produce(make_slice(w.wgu, 2 * I, H, 2), ring, q);
                 produce(make_slice(w.wdown, H, I, 1), ring, q);
@@ -260,7 +280,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     }
 
     // ------------------------------ consumers ------------------------------
-    const int pos = __ldcg(p.pos);
     const int HD = 128, half = 64;
     const float* cs = p.rope_cos + (size_t)pos * half;
     const float* sn = p.rope_sin + (size_t)pos * half;
@@ -275,97 +294,104 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
         norm_to_smem(p.x, w.ln_in, H, p.eps, xs, red);
         consume<H, ME_STORE>(make_slice(w.wqkv, QD + 2 * p.KVD, H, 1), ring, q, xs, p.qkv, best_v, best_i);
         bar_target += G; grid_sync(p.bar, bar_target);
-        // ---- phase 2: attention partials, work item = (kv head, ctx split) ----
-        if ((int)blockIdx.x < p.nkv * p.nsplit) {
-            const int g = blockIdx.x / p.nsplit, sp = blockIdx.x % p.nsplit;
-            float* qs = xs;                       // [group][128]
-            float* kn = qs + p.group * HD;        // [128]
-            float* vn = kn + HD;                  // [128]
-            float* sc = vn + HD;                  // [group][MAX_SPLIT_KEYS]
-            float* kc = p.kcache + (size_t)l * p.cache_layer_stride + (size_t)g * p.max_ctx * HD;
-            float* vc = p.vcache + (size_t)l * p.cache_layer_stride + (size_t)g * p.max_ctx * HD;
-            if (warp < p.group) head_norm_rope(p.qkv + (size_t)(g * p.group + warp) * HD, w.qnorm, p.eps, cs, sn, qs + warp * HD, lane);
-            else if (warp == p.group) head_norm_rope(p.qkv + QD + (size_t)g * HD, w.knorm, p.eps, cs, sn, kn, lane);
-            else if (warp == p.group + 1) {
+        // ---- phase 2: attention partials, work item = (kv head, 64-key split) ----
+        {
+            const int nk = pos + 1;                              // keys 0..pos
+            const int nloc = att_cta ? max(0, min(nk - att_j0, KV_KEYS)) : 0;   // keys of this split incl. the new one
+            if (nloc > 0) {
+                const int g = att_g;
+                float* qs = xs;                       // [group][128]
+                float* kn = qs + p.group * HD;        // [128]
+                float* vn = kn + HD;                  // [128]
+                float* sc = vn + HD;                  // [group][KV_KEYS]
+                float* ex = sc + p.group * KV_KEYS;   // [group][128]
+                float* Ks = reinterpret_cast<float*>(kv_smem);
+                float* Vs = reinterpret_cast<float*>(kv_smem + KV_TILE_BYTES);
+                const bool has_new = (pos >= att_j0) && (pos < att_j0 + KV_KEYS);
+                if (warp < p.group) head_norm_rope(p.qkv + (size_t)(g * p.group + warp) * HD, w.qnorm, p.eps, cs, sn, qs + warp * HD, lane);
+                else if (warp == p.group && has_new) head_norm_rope(p.qkv + QD + (size_t)g * HD, w.knorm, p.eps, cs, sn, kn, lane);
+                else if (warp == p.group + 1 && has_new) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) vn[lane + 32 * i] = __ldcg(p.qkv + QD + p.KVD + (size_t)g * HD + lane + 32 * i);
-            }
-            cons_sync();
-            if (sp == 0 && tid < HD) {            // KV append (replaces Tensor::cat, layers.rs:311-317)
-                kc[(size_t)pos * HD + tid] = kn[tid];
-                vc[(size_t)pos * HD + tid] = vn[tid];
-            }
-            const int nk = pos + 1;
-            const int Lk = (nk + p.nsplit - 1) / p.nsplit;
-            const int j0 = sp * Lk, j1 = min(nk, j0 + Lk);
-            const float div = sqrtf((float)HD);
-            for (int j = j0 + warp; j < j1; j += NCONS_WARPS) {
-                float4 kv;
-                if (j == pos) kv = *reinterpret_cast<const float4*>(kn + lane * 4);
-                else kv = __ldcg(reinterpret_cast<const float4*>(kc + (size_t)j * HD) + lane);
-                for (int hq = 0; hq < p.group; ++hq) {
-                    const float4 qv = *reinterpret_cast<const float4*>(qs + hq * HD + lane * 4);
-                    float dot = warp_sum(kv.x * qv.x + kv.y * qv.y + kv.z * qv.z + kv.w * qv.w);
-                    if (lane == 0) sc[hq * MAX_SPLIT_KEYS + (j - j0)] = dot / div;
+                    for (int i = 0; i < 4; ++i) vn[lane + 32 * i] = __ldcg(p.qkv + QD + p.KVD + (size_t)g * HD + lane + 32 * i);
                 }
-            }
-            cons_sync();
-            const int nkeys = max(0, j1 - j0);
-            // softmax partials: warp hq handles head hq (group <= 8)
-            if (warp < p.group) {
-                float mx = -INFINITY;
-                for (int j = lane; j < nkeys; j += 32) mx = fmaxf(mx, sc[warp * MAX_SPLIT_KEYS + j]);
-                mx = warp_max(mx);
-                float sum = 0.f;
-                for (int j = lane; j < nkeys; j += 32) {
-                    float e = expf(sc[warp * MAX_SPLIT_KEYS + j] - mx);
-                    sc[warp * MAX_SPLIT_KEYS + j] = e; sum += e;
-                }
-                sum = warp_sum(sum);
-                if (lane == 0) {
-                    float* pp = p.attn_part + ((size_t)blockIdx.x * p.group + warp) * PSTRIDE;
-                    pp[HD] = nkeys > 0 ? mx : -INFINITY; pp[HD + 1] = sum;
-                }
-            }
-            cons_sync();
-            // o[hq][d] = sum_j e[hq][j] * V[j][d]; thread = (d, key parity half)
-            {
-                const int d = tid & (HD - 1), part = tid >> 7;           // 2 partitions of keys
-                float acc[8];
-#pragma unroll
-                for (int hq = 0; hq < 8; ++hq) acc[hq] = 0.f;
-                for (int j = part; j < nkeys; j += 2) {
-                    const int jj = j0 + j;
-                    const float vv = (jj == pos) ? vn[d] : __ldcg(vc + (size_t)jj * HD + d);
-#pragma unroll
-                    for (int hq = 0; hq < 8; ++hq) if (hq < p.group) acc[hq] = fmaf(sc[hq * MAX_SPLIT_KEYS + j], vv, acc[hq]);
-                }
-                float* ex = sc + p.group * MAX_SPLIT_KEYS;               // [group][128] exchange
+                if (n_old > 0) mbar_wait(kv_full, kvq & 1);      // prefetched K/V tiles have landed
                 cons_sync();
-                if (part == 1) for (int hq = 0; hq < p.group; ++hq) ex[hq * HD + d] = acc[hq];
+                if (has_new && tid < HD) {            // KV append (replaces Tensor::cat, layers.rs:311-317)
+                    float* kc = p.kcache + (size_t)l * p.cache_layer_stride + ((size_t)g * p.max_ctx + pos) * HD;
+                    float* vc = p.vcache + (size_t)l * p.cache_layer_stride + ((size_t)g * p.max_ctx + pos) * HD;
+                    const float kx = kn[tid], vx = vn[tid];
+                    kc[tid] = kx; vc[tid] = vx;
+                    Ks[(pos - att_j0) * HD + tid] = kx; Vs[(pos - att_j0) * HD + tid] = vx;
+                }
                 cons_sync();
-                if (part == 0)
-                    for (int hq = 0; hq < p.group; ++hq)
-                        p.attn_part[((size_t)blockIdx.x * p.group + hq) * PSTRIDE + d] = acc[hq] + ex[hq * HD + d];
+                const float div = sqrtf((float)HD);
+                for (int j = warp; j < nloc; j += NCONS_WARPS) {
+                    const float4 kv = *reinterpret_cast<const float4*>(Ks + j * HD + lane * 4);
+                    for (int hq = 0; hq < p.group; ++hq) {
+                        const float4 qv = *reinterpret_cast<const float4*>(qs + hq * HD + lane * 4);
+                        float dot = warp_sum(kv.x * qv.x + kv.y * qv.y + kv.z * qv.z + kv.w * qv.w);
+                        if (lane == 0) sc[hq * KV_KEYS + j] = dot / div;
+                    }
+                }
+                cons_sync();
+                if (warp < p.group) {                 // softmax partial of head `warp` over this split
+                    float mx = -INFINITY;
+                    for (int j = lane; j < nloc; j += 32) mx = fmaxf(mx, sc[warp * KV_KEYS + j]);
+                    mx = warp_max(mx);
+                    float sum = 0.f;
+                    for (int j = lane; j < nloc; j += 32) {
+                        float e = expf(sc[warp * KV_KEYS + j] - mx);
+                        sc[warp * KV_KEYS + j] = e; sum += e;
+                    }
+                    sum = warp_sum(sum);
+                    if (lane == 0) {
+                        float* pp = p.attn_part + ((size_t)blockIdx.x * p.group + warp) * PSTRIDE;
+                        pp[HD] = mx; pp[HD + 1] = sum;
+                    }
+                }
+                cons_sync();
+                {   // o[hq][d] = sum_j e[hq][j] * V[j][d]; thread = (d, key-parity partition)
+                    const int d = tid & (HD - 1), part = tid >> 7;
+                    float acc[8];
+#pragma unroll
+                    for (int hq = 0; hq < 8; ++hq) acc[hq] = 0.f;
+                    for (int j = part; j < nloc; j += 2) {
+                        const float vv = Vs[j * HD + d];
+#pragma unroll
+                        for (int hq = 0; hq < 8; ++hq) if (hq < p.group) acc[hq] = fmaf(sc[hq * KV_KEYS + j], vv, acc[hq]);
+                    }
+                    if (part == 1) for (int hq = 0; hq < p.group; ++hq) ex[hq * HD + d] = acc[hq];
+                    cons_sync();
+                    if (part == 0)
+                        for (int hq = 0; hq < p.group; ++hq)
+                            p.attn_part[((size_t)blockIdx.x * p.group + hq) * PSTRIDE + d] = acc[hq] + ex[hq * HD + d];
+                }
+                if (n_old > 0) {                      // hand the K/V staging buffer back to the producer
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(kv_empty);
+                    ++kvq;
+                }
             }
         }
         bar_target += G; grid_sync(p.bar, bar_target);
         // ---- phase 3: merge attention partials -> o_proj GEMV + residual ----
-        for (int o = tid; o < QD; o += NCONS) {
-            const int h = o / HD, d = o - h * HD;
-            const int g = h / p.group, hq = h - g * p.group;
-            float M = -INFINITY;
-            for (int s = 0; s < p.nsplit; ++s) M = fmaxf(M, __ldcg(p.attn_part + ((size_t)(g * p.nsplit + s) * p.group + hq) * PSTRIDE + HD));
-            float Lsum = 0.f, O = 0.f;
-            for (int s = 0; s < p.nsplit; ++s) {
-                const float* pp = p.attn_part + ((size_t)(g * p.nsplit + s) * p.group + hq) * PSTRIDE;
-                const float ms = __ldcg(pp + HD);
-                if (ms == -INFINITY) continue;
-                const float sc_ = expf(ms - M);
-                Lsum = fmaf(__ldcg(pp + HD + 1), sc_, Lsum);
-                O = fmaf(__ldcg(pp + d), sc_, O);
+        {
+            const int nact = min(p.nsplit, (pos + KV_KEYS) / KV_KEYS);     // splits holding at least one of keys 0..pos
+            for (int o = tid; o < QD; o += NCONS) {
+                const int h = o / HD, d = o - h * HD;
+                const int g = h / p.group, hq = h - g * p.group;
+                float M = -INFINITY;
+                for (int s2 = 0; s2 < nact; ++s2) M = fmaxf(M, __ldcg(p.attn_part + ((size_t)(g * p.nsplit + s2) * p.group + hq) * PSTRIDE + HD));
+                float Lsum = 0.f, O = 0.f;
+                for (int s2 = 0; s2 < nact; ++s2) {
+                    const float* pp = p.attn_part + ((size_t)(g * p.nsplit + s2) * p.group + hq) * PSTRIDE;
+                    const float sc_ = expf(__ldcg(pp + HD) - M);
+                    Lsum = fmaf(__ldcg(pp + HD + 1), sc_, Lsum);
+                    O = fmaf(__ldcg(pp + d), sc_, O);
+                }
+                xs[o] = O / Lsum;
             }
-            xs[o] = O / Lsum;
         }
         cons_sync();
         consume<QD, ME_RESID>(make_slice(w.wo, H, QD, 1), ring, q, xs, p.x, best_v, best_i);
@@ -444,20 +470,22 @@ struct MegaState {
 static MegaState g_mega;   // one model per process in practice; re-created when the model changes
 
 static size_t mega_smem_bytes() {
-    return (size_t)mega::NSLOT * mega::SLOT_BYTES + mega::XS_FLOATS * 4 + 2 * mega::NSLOT * 8 + 64 * 4 + 64 * 4 + 64;
+    return (size_t)mega::NSLOT * mega::SLOT_BYTES + 2 * mega::KV_TILE_BYTES + mega::XS_FLOATS * 4 + (2 * mega::NSLOT + 2) * 8 +
+           64 * 4 + 64 * 4 + 64;
 }
 
 template <int H, int QD, int I> static bool dims_match(const asrb_dims& c) {
     return c.hidden_size == H && c.num_attention_heads * c.head_dim == QD && c.intermediate_size == I;
 }
 
-bool decode_mega_supported(const Model& m, int B) {
+bool decode_mega_supported(const Model& m, int B, int max_ctx) {
     const asrb_dims& c = m.d.c;
     if (B != 1 || c.head_dim != 128) return false;
     const int group = c.num_attention_heads / c.num_key_value_heads;
     if (group + 2 > mega::NCONS_WARPS) return false;
-    if ((size_t)(group * 128 + 256 + group * mega::MAX_SPLIT_KEYS + group * 128) > (size_t)mega::XS_FLOATS) return false;
+    if ((size_t)(group * 128 + 256 + group * mega::KV_KEYS + group * 128) > (size_t)mega::XS_FLOATS) return false;
     if (m.ctx->smem_optin < mega_smem_bytes()) return false;
+    if (((max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS) * c.num_key_value_heads > m.ctx->sm_count) return false;   // one CTA per (kv head, 64-key split)
     return dims_match<1024, 2048, 3072>(c) || dims_match<256, 512, 512>(c);
 }
 
@@ -465,12 +493,11 @@ void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* 
                              size_t cache_layer_stride, size_t cache_seq_stride, int max_ctx, cudaStream_t st,
                              int64_t* launches) {
     (void)cache_seq_stride;
-    ASRB_REQUIRE(decode_mega_supported(m, B), ASRB_ERR_STATE, "fused decode step not supported for this model/batch");
+    ASRB_REQUIRE(decode_mega_supported(m, B, max_ctx), ASRB_ERR_STATE, "fused decode step not supported for this model/batch");
     const asrb_dims& c = m.d.c;
     const int G = m.ctx->sm_count;
     const int group = c.num_attention_heads / c.num_key_value_heads;
-    int nsplit = std::max(1, std::min(G / c.num_key_value_heads, 4));
-    while ((max_ctx + nsplit - 1) / nsplit > mega::MAX_SPLIT_KEYS) ++nsplit;
+    const int nsplit = (max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS;
     ASRB_REQUIRE(nsplit * c.num_key_value_heads <= G, ASRB_ERR_INVALID, "context too long for the fused decode step");
     if (g_mega.model != &m) {
         if (g_mega.d_layers) { cudaFree(g_mega.d_layers); cudaFree(g_mega.d_bar); g_mega.d_layers = nullptr; }

@@ -91,6 +91,9 @@ Session* session_create(Model* m, int max_batch, int64_t max_samples, int max_la
     Session* s = new Session();
     try {
         const Dims& d = m->d; const asrb_dims& c = d.c;
+        if (const char* e = getenv("ASRB_GEMM")) s->gemm_impl = (std::string(e) == "simt") ? GEMM_SIMT : GEMM_TC;     // debug overrides
+        if (const char* e = getenv("ASRB_DECODE")) s->decode_mode = (std::string(e) == "phases") ? 0 : 1;
+        if (const char* e = getenv("ASRB_PLANES")) s->nplanes = std::min(3, std::max(1, atoi(e)));
         s->m = m; s->max_batch = max_batch; s->max_samples = max_samples; s->max_lang = max_lang; s->max_new = max_new;
         s->max_npad = ((max_samples + 159) / 160) * 160;
         s->maxF = (int)(s->max_npad / 160);
@@ -416,7 +419,7 @@ void session_prefill(Session* s, const int64_t* const* lang_ids, const int32_t* 
 // -------------------------------------------------------------------------------------------------
 // step 8: greedy loop  (inference.rs:160-200)
 // -------------------------------------------------------------------------------------------------
-bool decode_mega_supported(const Model& m, int B);
+bool decode_mega_supported(const Model& m, int B, int max_ctx);
 void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* kcache, float* vcache,
                              size_t cache_layer_stride, size_t cache_seq_stride, int max_ctx, cudaStream_t st,
                              int64_t* launches);
@@ -424,7 +427,7 @@ void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* 
 // one iteration of the loop body: decoder forward on the pending token, then the greedy bookkeeping
 // that selects / appends / embeds the next one.  (The fused kernel does both.)
 static bool use_mega(Session* s, bool write_logits) {
-    return s->decode_mode == 1 && !write_logits && decode_mega_supported(*s->m, s->B);
+    return s->decode_mode == 1 && !write_logits && decode_mega_supported(*s->m, s->B, s->max_ctx);
 }
 static void forward_step(Session* s, bool write_logits) {
     Model& m = *s->m;
