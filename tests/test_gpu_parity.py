@@ -191,3 +191,25 @@ def test_full_size_0p6b_one_clip(report):
         assert got.ids[0] == ref.ids
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("shards", [1, 3])
+def test_model_load_from_directory(tiny, tmp_path, shards):
+    """AsrInference::load (inference.rs:30-86): config.json + model.safetensors / sharded index
+    (weights.rs:10-58) parsed by the C++ loader must behave exactly like in-memory construction."""
+    from qwen3_asr_rs_b200 import AsrInference
+    from qwen3_asr_rs_b200._lib import AsrbError
+    cfg, w, model = tiny
+    d = tmp_path / f"model{shards}"
+    synth.write_checkpoint(str(d), cfg, w, shards=shards)
+    x = synth.make_clip(95, 3.3)
+    ref = O.transcribe_ids(model, x, max_new_tokens=10)
+    eng = AsrInference.load(str(d), device=0)
+    try:
+        assert eng.config.text.hidden_size == 256 and eng.config.audio.d_model == 128
+        got = eng.transcribe_ids([x], max_new_tokens=10)
+    finally:
+        eng.close()
+    assert got.ids[0] == ref.ids
+    with pytest.raises(AsrbError):
+        AsrInference.load(str(tmp_path / "does_not_exist"), device=0)
