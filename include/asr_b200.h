@@ -137,6 +137,10 @@ ASRB_API int asrb_last_timings(asrb_session* s, float* ms_out6, int64_t* kernels
  * "resident" = "1"|"0" (1: the samples uploaded by the previous call are reused, no H2D) */
 ASRB_API int asrb_session_set_option(asrb_session* s, const char* key, const char* value);
 
+/* debug (ASRB_MEGA_DEBUG=1): clock64 timeline of the last fused decode step, CTA 0 then CTA G-1;
+ * returns the number of slots per CTA (0 if disabled) */
+ASRB_API int asrb_debug_mega_timeline(long long* out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ void session_transcribe_ids(Session* s, const float* const* samples, const int64
                             int32_t* ids_out, int32_t* lens_out);
 void session_last_timings(Session* s, float* ms6, int64_t* kernels, int64_t* steps);
 void session_set_option(Session* s, const char* key, const char* value);
+int decode_mega_debug_timeline(long long* out, int cap);
 }  // namespace asrb
 
 using namespace asrb;
@@ -149,6 +150,12 @@ int asrb_last_timings(asrb_session* s, float* ms_out6, int64_t* kernels_launched
 }
 int asrb_session_set_option(asrb_session* s, const char* key, const char* value) {
     return guarded([&] { NONNULL(s); session_set_option(s->s, key, value); });
+}
+
+int asrb_debug_mega_timeline(long long* out, int cap) {
+    int n = 0;
+    guarded([&] { n = decode_mega_debug_timeline(out, cap); });
+    return n;
 }
 
 }  // extern "C"

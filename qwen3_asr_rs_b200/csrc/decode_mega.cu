@@ -46,7 +46,9 @@ struct Params {
     float* part_val; int* part_idx;     // [gridDim.x]
     int* pos; int* done; int* next_id; int* ids_out; int* n_out; int max_new;
     unsigned* bar;               // [0] grid barrier counter, [1] finish ticket
+    long long* dbg;              // optional timeline [2][DBG_SLOTS] of clock64 (CTA 0 and CTA G-1), else null
 };
+static constexpr int DBG_SLOTS = 512;
 
 // ---- PTX helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -224,6 +226,11 @@ __device__ __forceinline__ void head_norm_rope(const float* __restrict__ src, co
     }
 }
 
+#define MEGA_MARK()                                                                                    \
+    do {                                                                                               \
+        if (dbg_row && tid == 0 && dbg_i < DBG_SLOTS) dbg_row[dbg_i++] = clock64();                    \
+    } while (0)
+
 template <int H, int QD, int I>
 __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -280,6 +287,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     }
 
     // ------------------------------ consumers ------------------------------
+    long long* dbg_row = nullptr; int dbg_i = 0;
+    if (p.dbg && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) dbg_row = p.dbg + (blockIdx.x == 0 ? 0 : DBG_SLOTS);
+    MEGA_MARK();
     const int HD = 128, half = 64;
     const float* cs = p.rope_cos + (size_t)pos * half;
     const float* sn = p.rope_sin + (size_t)pos * half;
@@ -293,7 +303,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
         // ---- phase 1: RMSNorm + [q|k|v] GEMV ----
         norm_to_smem(p.x, w.ln_in, H, p.eps, xs, red);
         consume<H, ME_STORE>(make_slice(w.wqkv, QD + 2 * p.KVD, H, 1), ring, q, xs, p.qkv, best_v, best_i);
+        MEGA_MARK();
         bar_target += G; grid_sync(p.bar, bar_target);
+        MEGA_MARK();
         // ---- phase 2: attention partials, work item = (kv head, 64-key split) ----
         {
             const int nk = pos + 1;                              // keys 0..pos
@@ -374,7 +386,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                 }
             }
         }
+        MEGA_MARK();
         bar_target += G; grid_sync(p.bar, bar_target);
+        MEGA_MARK();
         // ---- phase 3: merge attention partials -> o_proj GEMV + residual ----
         {
             const int nact = min(p.nsplit, (pos + KV_KEYS) / KV_KEYS);     // splits holding at least one of keys 0..pos
@@ -395,20 +409,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
         }
         cons_sync();
         consume<QD, ME_RESID>(make_slice(w.wo, H, QD, 1), ring, q, xs, p.x, best_v, best_i);
+        MEGA_MARK();
         bar_target += G; grid_sync(p.bar, bar_target);
+        MEGA_MARK();
         // ---- phase 4: RMSNorm + gate/up GEMV + SiLU*mul ----
         norm_to_smem(p.x, w.ln_post, H, p.eps, xs, red);
         consume<H, ME_SWIGLU>(make_slice(w.wgu, 2 * I, H, 2), ring, q, xs, p.act, best_v, best_i);
+        MEGA_MARK();
         bar_target += G; grid_sync(p.bar, bar_target);
+        MEGA_MARK();
         // ---- phase 5: down GEMV + residual ----
         for (int i = tid; i < I; i += NCONS) xs[i] = __ldcg(p.act + i);
         cons_sync();
         consume<I, ME_RESID>(make_slice(w.wdown, H, I, 1), ring, q, xs, p.x, best_v, best_i);
+        MEGA_MARK();
         bar_target += G; grid_sync(p.bar, bar_target);
+        MEGA_MARK();
     }
     // ---- final RMSNorm + tied lm_head GEMV + argmax ----
     norm_to_smem(p.x, p.final_norm, H, p.eps, xs, red);
     consume<H, ME_ARGMAX>(make_slice(p.lm_head, p.V, H, 1), ring, q, xs, nullptr, best_v, best_i);
+    MEGA_MARK();
     // every lane of a warp saw the same values: lane 0 publishes the warp's best
     cons_sync();
     if (lane == 0) { red[warp] = best_v; ired[warp] = best_i; }
@@ -464,7 +485,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
 
 // host side ---------------------------------------------------------------------------------------
 struct MegaState {
-    DecLayerW* d_layers = nullptr; unsigned* d_bar = nullptr; float* d_part = nullptr;
+    DecLayerW* d_layers = nullptr; unsigned* d_bar = nullptr; float* d_part = nullptr; long long* d_dbg = nullptr;
     int part_cap = 0; const Model* model = nullptr;
 };
 static MegaState g_mega;   // one model per process in practice; re-created when the model changes
@@ -523,6 +544,11 @@ void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* 
     p.part_val = b.part_val; p.part_idx = b.part_idx;
     p.pos = b.pos; p.done = b.done; p.next_id = b.next_id; p.ids_out = b.ids_out; p.n_out = b.n_out; p.max_new = b.max_new;
     p.bar = g_mega.d_bar;
+    if (getenv("ASRB_MEGA_DEBUG")) {
+        if (!g_mega.d_dbg) { ASRB_CUDA_CHECK(cudaMalloc(&g_mega.d_dbg, 2 * mega::DBG_SLOTS * sizeof(long long)));
+                             ASRB_CUDA_CHECK(cudaMemset(g_mega.d_dbg, 0, 2 * mega::DBG_SLOTS * sizeof(long long))); }
+        p.dbg = g_mega.d_dbg;
+    }
     const size_t smem = mega_smem_bytes();
     void* args[] = {(void*)&p};
     const void* fn = nullptr;
@@ -531,6 +557,14 @@ void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* 
     ASRB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ASRB_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(mega::NTHREADS), args, smem, st));
     if (launches) *launches += 1;
+}
+
+// debug: copy the clock64 timeline of the most recent fused step (CTA 0 then CTA G-1), returns slots per CTA
+int decode_mega_debug_timeline(long long* out, int cap) {
+    if (!g_mega.d_dbg || cap < 2 * mega::DBG_SLOTS) return 0;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, g_mega.d_dbg, 2 * mega::DBG_SLOTS * sizeof(long long), cudaMemcpyDeviceToHost);
+    return mega::DBG_SLOTS;
 }
 
 }  // namespace asrb

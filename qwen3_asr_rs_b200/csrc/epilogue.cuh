@@ -94,3 +94,78 @@ __device__ __forceinline__ float load_a(const GemmA& A, int m, int k) {
 }
 
 }  // namespace asrb
+
+// ---------------------------------------------------------------------------------------------
+// Vectorised epilogue for the tensor-core GEMM: one thread owns 8 consecutive accumulator columns
+// n..n+7 (n % 8 == 0) of row m.  Same arithmetic as epi_store2; stores are 128-bit where the layout
+// allows (fp32 rows: 2 x float4, split3 planes: one uint4 of 8 bf16 per plane).
+// ---------------------------------------------------------------------------------------------
+namespace asrb {
+
+__device__ __forceinline__ void store_split3_x8(bf16* base, size_t plane_stride, size_t idx, const float* v) {
+    uint32_t hi[4], mid[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        Split3 a = split3(v[2 * i]), b = split3(v[2 * i + 1]);
+        hi[i] = (uint32_t)__bfloat16_as_ushort(a.hi) | ((uint32_t)__bfloat16_as_ushort(b.hi) << 16);
+        mid[i] = (uint32_t)__bfloat16_as_ushort(a.mid) | ((uint32_t)__bfloat16_as_ushort(b.mid) << 16);
+        lo[i] = (uint32_t)__bfloat16_as_ushort(a.lo) | ((uint32_t)__bfloat16_as_ushort(b.lo) << 16);
+    }
+    *reinterpret_cast<uint4*>(base + idx) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + plane_stride + idx) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+    *reinterpret_cast<uint4*>(base + 2 * plane_stride + idx) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+template <int MODE>
+__device__ __forceinline__ void epi_store8(const GemmEpi& e, int N, int m, int n, const float* acc) {
+    if (MODE == EPI_PLAIN) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = acc[i];
+        if (e.bias) {
+            const float4 b0 = *reinterpret_cast<const float4*>(e.bias + n), b1 = *reinterpret_cast<const float4*>(e.bias + n + 4);
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (e.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+        }
+        if (e.residual) {
+            const float* r = e.residual + (size_t)m * e.ldr + n;
+            const float4 r0 = *reinterpret_cast<const float4*>(r), r1 = *reinterpret_cast<const float4*>(r + 4);
+            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        }
+        if (e.out_f32) {
+            float* o = e.out_f32 + (size_t)m * e.ldo + n;
+            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        if (e.out_s3) store_split3_x8(e.out_s3, e.s3_plane_stride, (size_t)m * e.lds + n, v);
+    } else if (MODE == EPI_CONV_PARITY) {
+        const int per = e.OH * e.OW;
+        const int chunk = m / per, r = m - chunk * per;
+        const int oh = r / e.OW, ow = r - oh * e.OW;
+        size_t base = ((((size_t)chunk * 2 + (oh & 1)) * 2 + (ow & 1)) * e.Hh2 + (oh >> 1)) * e.Wh2 + (ow >> 1);
+        base = base * e.cpad + n;
+        float v[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(e.bias + n), b1 = *reinterpret_cast<const float4*>(e.bias + n + 4);
+        v[0] = gelu_erf(acc[0] + b0.x); v[1] = gelu_erf(acc[1] + b0.y); v[2] = gelu_erf(acc[2] + b0.z); v[3] = gelu_erf(acc[3] + b0.w);
+        v[4] = gelu_erf(acc[4] + b1.x); v[5] = gelu_erf(acc[5] + b1.y); v[6] = gelu_erf(acc[6] + b1.z); v[7] = gelu_erf(acc[7] + b1.w);
+        store_split3_x8(e.out_s3, e.s3_plane_stride, base, v);
+    } else if (MODE == EPI_CONVOUT) {
+        const int tok = e.row_map[m];
+        if (tok < 0) return;
+        const int t = m % e.pos_period;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = acc[i] + (e.bias ? e.bias[n + i] : 0.f) + e.pos[(size_t)t * N + n + i];
+        float* o = e.out_f32 + (size_t)tok * e.ldo + n;
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {   // EPI_SWIGLU (4 outputs from 8 columns) and EPI_CONV_FEAT (strided): pairwise path
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) epi_store2(e, N, m, n + i, acc[i], acc[i + 1], true);
+    }
+}
+
+}  // namespace asrb

@@ -31,7 +31,8 @@ static constexpr int TILE_A_BYTES = BM * BK * 2;      // 16 KB per plane
 static constexpr int TILE_B_BYTES = BN * BK * 2;      // 16 KB
 static constexpr int STAGE_BYTES = 3 * TILE_A_BYTES + TILE_B_BYTES;   // 64 KB
 static constexpr int NTHREADS = 192;                  // warp0 TMA, warp1 MMA, warps 2-5 epilogue
-static constexpr int TMEM_COLS = 128;
+static constexpr int TMEM_COLS = 256;                 // two 128-column fp32 accumulators (ping-pong)
+static constexpr int CH = 4;                          // k-blocks (of 64) accumulated inside the tensor core per chunk
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -110,7 +111,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 struct ConvGeom { int OH, OW, box_h, tiles_per_chunk, kblk_per_tap, a_box_bytes; };
 
 // A_MODE 0: plain [planes][M][K];  1: conv taps over the parity layout
-template <int A_MODE>
+//
+// Accumulation: tcgen05 adds products into the fp32 TMEM accumulator with round-toward-zero, which
+// biases long-K sums (measured on the 0.6B model: logits 1.3e-4 rel vs 1.3e-5 for an fp32 FMA GEMM).
+// So the tensor core only accumulates CH k-blocks (K = 256) at a time into one of two TMEM
+// accumulators; the epilogue warps drain each finished chunk with tcgen05.ld and add it into fp32
+// registers (round-to-nearest) while the MMA warp fills the other accumulator.
+template <int A_MODE, int EPI_MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                int M, int N, int K, int nplanes, ConvGeom cg, GemmEpi E) {
@@ -118,15 +125,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
-    uint64_t* acc_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    uint64_t* acc_full = empty + STAGES;      // [2]
+    uint64_t* acc_empty = acc_full + 2;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN;
     const int num_kb = K / BK;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(acc_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
@@ -173,41 +181,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t idesc = make_idesc();
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % STAGES; const uint32_t par = (kb / STAGES) & 1;
+            const int c = kb / CH, cb = c & 1;                          // chunk index / accumulator buffer
+            const bool chunk_first = (kb % CH) == 0;
+            if (chunk_first) { mbar_wait(&acc_empty[cb], ((c >> 1) & 1) ^ 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
             mbar_wait(&full[s], par);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
             const uint64_t bdesc = make_smem_desc(sa + 3 * TILE_A_BYTES);
+            const uint32_t tacc = tmem_base + (uint32_t)(cb * BN);
             for (int p = 0; p < nplanes; ++p) {
                 const uint64_t adesc = make_smem_desc(sa + p * TILE_A_BYTES);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)     // +32 B per K=16 step inside the 128 B swizzle atom
-                    umma(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | p | k) != 0);
+                    umma(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, !(chunk_first && p == 0 && k == 0));
             }
             umma_commit(&empty[s]);                   // slot reusable once these MMAs retire
+            if ((kb % CH) == CH - 1 || kb == num_kb - 1) umma_commit(&acc_full[cb]);
         }
-        umma_commit(acc_full);
     } else if (warp >= 2) {
         // ================= epilogue =================
-        mbar_wait(acc_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
         const int r = quad * 32 + lane;               // row inside the tile
+        float accum[BN];
+#pragma unroll
+        for (int j = 0; j < BN; ++j) accum[j] = 0.f;
+        const int num_chunks = (num_kb + CH - 1) / CH;
+        for (int c = 0; c < num_chunks; ++c) {
+            const int cb = c & 1;
+            mbar_wait(&acc_full[cb], (c >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * BN + c0), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) accum[c0 + j] += __uint_as_float(v[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[cb])) : "memory");
+        }
         long long m = -1;
         if (A_MODE == 0) { if (m0 + r < M) m = m0 + r; }
         else {
             const int oh = oh0 + r / cg.OW, ow = r % cg.OW;
             if (r < cg.box_h * cg.OW && oh < cg.OH) m = ((long long)chunk * cg.OH + oh) * cg.OW + ow;
         }
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-            if (m >= 0) {
+        if (m >= 0) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const int n = n0 + c0 + j;
-                    if (n < N) epi_store2(E, N, (int)m, n, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), n + 1 < N);
-                }
+            for (int j = 0; j < BN; j += 8) {
+                const int n = n0 + j;
+                if (n < N) epi_store8<EPI_MODE>(E, N, (int)m, n, &accum[j]);
             }
         }
     }
@@ -244,7 +268,7 @@ static CUtensorMap make_map(const void* base, int rank, const cuuint64_t* dims, 
     return m;
 }
 
-static size_t smem_bytes() { return (size_t)STAGES * STAGE_BYTES + 1024 + 256; }
+static size_t smem_bytes() { return (size_t)STAGES * STAGE_BYTES + 1024 + 256; }   // stages + alignment slack + barriers
 
 }  // namespace tc
 
@@ -260,16 +284,24 @@ bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& E, cuda
     CUtensorMap mapB = make_map(W, 2, bd, bs, bb);
     ConvGeom cg{};
     const size_t smem = smem_bytes();
+    if (N % 8 != 0) return false;
     if (A.mode == A_PLAIN) {
         if (A.plane_stride % 8 != 0 && A.nplanes > 1) return false;
         cuuint64_t ad[3] = {(cuuint64_t)A.K, (cuuint64_t)A.M, (cuuint64_t)3};
         cuuint64_t as[2] = {(cuuint64_t)A.lda * 2, (cuuint64_t)A.plane_stride * 2};
         cuuint32_t ab[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1};
         CUtensorMap mapA = make_map(A.a, 3, ad, as, ab);
-        static bool attr = false;
-        if (!attr) { ASRB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
         dim3 grid((N + BN - 1) / BN, (A.M + BM - 1) / BM);
-        gemm_tc_kernel<0><<<grid, NTHREADS, smem, st>>>(mapA, mapB, A.M, N, A.K, A.nplanes, cg, E);
+#define ASRB_TC_LAUNCH(AM, EM)                                                                                         \
+    {                                                                                                                  \
+        static bool attr = false;                                                                                      \
+        if (!attr) { ASRB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<AM, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
+        gemm_tc_kernel<AM, EM><<<grid, NTHREADS, smem, st>>>(mapA, mapB, A.M, N, A.K, A.nplanes, cg, E);                \
+    }
+        if (E.mode == EPI_PLAIN) ASRB_TC_LAUNCH(0, EPI_PLAIN)
+        else if (E.mode == EPI_SWIGLU) ASRB_TC_LAUNCH(0, EPI_SWIGLU)
+        else if (E.mode == EPI_CONVOUT) ASRB_TC_LAUNCH(0, EPI_CONVOUT)
+        else return false;
     } else {
         if (A.cpad % BK != 0 || A.OW > BM) return false;
         const int per = A.OH * A.OW;
@@ -283,10 +315,11 @@ bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& E, cuda
                             (cuuint64_t)A.plane_stride * 2};
         cuuint32_t ab[5] = {(cuuint32_t)BK, (cuuint32_t)A.OW, (cuuint32_t)cg.box_h, 1, 1};
         CUtensorMap mapA = make_map(A.a, 5, ad, as, ab);
-        static bool attr = false;
-        if (!attr) { ASRB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
         dim3 grid((N + BN - 1) / BN, chunks * cg.tiles_per_chunk);
-        gemm_tc_kernel<1><<<grid, NTHREADS, smem, st>>>(mapA, mapB, A.M, N, A.K, A.nplanes, cg, E);
+        if (E.mode == EPI_CONV_PARITY) ASRB_TC_LAUNCH(1, EPI_CONV_PARITY)
+        else if (E.mode == EPI_CONV_FEAT) ASRB_TC_LAUNCH(1, EPI_CONV_FEAT)
+        else return false;
+#undef ASRB_TC_LAUNCH
     }
     ASRB_CUDA_CHECK(cudaGetLastError());
     return true;

@@ -1,0 +1,33 @@
+"""Debug: per-phase clock64 timeline of the fused decode step (ASRB_MEGA_DEBUG=1)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+os.environ["ASRB_MEGA_DEBUG"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from qwen3_asr_rs_b200 import AsrInference, _lib, config_0p6b, synth  # noqa: E402
+
+cfg = config_0p6b()
+eng = AsrInference.from_weights(cfg, synth.make_weights(cfg, 1), device=0)
+x = synth.make_clip(0, 30.0)
+for _ in range(2):
+    r = eng.transcribe_ids([x], max_new_tokens=32)
+print("stage_ms", r.stage_ms, "us/step", 1e3 * r.stage_ms["decode"] / max(r.decode_steps, 1))
+lib = _lib.load_library()
+buf = (C.c_longlong * 1024)()
+n = lib.asrb_debug_mega_timeline(buf, 1024)
+t = np.array(buf[:], dtype=np.int64).reshape(2, -1)
+L = cfg.text.num_hidden_layers
+names = ["p1_qkv", "bar1", "p2_attn", "bar2", "p3_oproj", "bar3", "p4_gateup", "bar4", "p5_down", "bar5"]
+for cta, row in zip(("cta0", "ctaLast"), t):
+    marks = row[: 2 + 10 * L]
+    d = np.diff(marks)
+    per = d[: 10 * L].reshape(L, 10)
+    print(cta, "total cycles", int(marks[-1] - marks[0]), " lm_head cycles", int(d[10 * L]))
+    print("  mean cycles per phase over layers:")
+    for i, nm in enumerate(names):
+        print(f"    {nm:10s} mean {per[:, i].mean():9.0f}  min {per[:, i].min():7d}  max {per[:, i].max():7d}")
+    print("  layer totals (first 4):", per.sum(1)[:4])
+eng.close()
