@@ -2,18 +2,24 @@
 //
 // Why: at batch 1 a decoder forward is 1.19 GB of weights read once (HBM-bound, ~190 us at the
 // measured 6.5 TB/s) but has ~141 dependent phases (28 layers x {qkv, attention, o_proj, gate/up,
-// down} + lm_head); launched as separate kernels each phase pays launch latency + a cold start of
-// the weight stream.  Here one CTA per SM stays resident for the whole step:
+// down} + lm_head).  As separate kernels each phase pays launch latency and a cold weight stream;
+// with device-wide barriers each phase pays an atomic + spin + re-read (measured: 1.4 ms/step).
+// Here one CTA per SM stays resident for the whole step:
 //   * a producer warp streams this CTA's slice of EVERY weight matrix, in phase order, into a
-//     shared-memory ring with cp.async.bulk (TMA bulk copy) + mbarrier transaction counts.  Weight
-//     addresses do not depend on activations, so the producer runs AHEAD across phase boundaries:
-//     HBM stays busy while consumers wait at a grid barrier.
+//     shared-memory ring with cp.async.bulk (TMA bulk copy) + mbarrier transaction counts, and the
+//     K/V rows of earlier positions into a staging tile.  None of these addresses depend on
+//     activations, so the producer runs AHEAD across phase boundaries: HBM stays busy while
+//     consumers wait for activations.
 //   * 8 consumer warps do the fp32 GEMV from shared memory (activation vector held in registers,
-//     bf16 -> fp32 up-cast is exact), phases separated by a device-wide barrier (one atomic + spin).
-//   * attention (QK-RMSNorm + RoPE + KV append + softmax.V) is split over kv-heads x ctx splits;
-//     partials are merged by the consumers of the o_proj phase.
+//     bf16 -> fp32 up-cast is exact, fp32 FMA accumulate).
+//   * activations are exchanged between CTAs WITHOUT barriers: every published fp32 value travels
+//     in an 8-byte {value, tag} word (tag = position/layer/phase), written with one 64-bit store and
+//     polled with 128-bit volatile loads until the tags match -- data and "ready" flag arrive in the
+//     same L2 round trip (the low-latency protocol of collective libraries, applied on-chip).
+//   * attention (QK-RMSNorm + RoPE + KV append + softmax.V) is split over kv-heads x 64-key tiles;
+//     the tile-0 CTA of each kv-head merges the partials and publishes the head outputs.
 //   * the last CTA to finish the lm_head performs the greedy bookkeeping (argmax, EOS, append,
-//     embedding of the next token), so no host sync and no extra launch per token.
+//     embedding of the next token), so there is no host sync and no extra launch per token.
 // Reference semantics per phase: see decode.cu.  Batch 1 only; other batches use decode.cu.
 #include "internal.h"
 
@@ -29,6 +35,13 @@ static constexpr int NSLOT = 5;                         // weight ring: 120 KB i
 static constexpr int KV_KEYS = 64;                      // keys per attention split (K and V tiles staged in smem)
 static constexpr int KV_TILE_BYTES = KV_KEYS * 128 * 4; // 32 KB each for K and V (fp32 cache)
 static constexpr int XS_FLOATS = 3072 + 64;             // activation vector / attention scratch
+static constexpr int XRES_MAX = 64;                     // residual rows owned by one CTA (H / gridDim.x, rounded up)
+static constexpr int HD = 128;
+static constexpr int PSTRIDE = HD + 2;                  // partial record: o[128], m, l
+static constexpr int DBG_SLOTS = 512;
+
+// phases (3 bits of the tag)
+enum { PH_QKV = 1, PH_PART = 2, PH_ATTN = 3, PH_XO = 4, PH_ACT = 5, PH_XD = 6 };
 
 struct Params {
     const DecLayerW* layers;     // device array [L]
@@ -38,17 +51,17 @@ struct Params {
     const float* rope_cos; const float* rope_sin;
     float eps;
     int L, H, QD, KVD, I, V, nq, nkv, group;
-    // state
-    float* x; float* qkv; float* act;
-    float* attn_part;            // [nkv*nsplit][group][HD+2]
+    // plain state (kernel-boundary visibility)
+    float* x;                    // [H] embedding of the pending token (in) / of the next token (out)
     float* kcache; float* vcache; size_t cache_layer_stride; int max_ctx;
     int nsplit;
     float* part_val; int* part_idx;     // [gridDim.x]
     int* pos; int* done; int* next_id; int* ids_out; int* n_out; int max_new;
-    unsigned* bar;               // [0] grid barrier counter, [1] finish ticket
+    unsigned* bar;               // [0] finish ticket, [1] launch epoch (starts at 1; 0 marks never-written words)
+    // tagged exchange buffers ({value, tag} words)
+    uint2* qkv_ll; uint2* part_ll; uint2* attn_ll; uint2* x_ll; uint2* act_ll;
     long long* dbg;              // optional timeline [2][DBG_SLOTS] of clock64 (CTA 0 and CTA G-1), else null
 };
-static constexpr int DBG_SLOTS = 512;
 
 // ---- PTX helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,22 +90,49 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+
+// ---- tagged exchange ({fp32 value, tag} in one 64-bit word) ------------------------------------
+__device__ __forceinline__ void ll_store(uint2* p, float v, uint32_t tag) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint4 ll_load2(const uint2* p) {      // two consecutive words (16-byte aligned)
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-// device-wide barrier among the consumer threads of all CTAs (all CTAs are co-resident:
-// cooperative launch, one CTA per SM)
-__device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned target) {
-    cons_sync();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
-        while (ld_acquire(ctr) < target) { }
-        __threadfence();
+__device__ __forceinline__ float ll_poll1(const uint2* p, uint32_t tag) {
+    uint2 v;
+    do {
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    } while (v.y != tag);
+    return __uint_as_float(v.x);
+}
+// all consumer threads: gather n (even) tagged values into shared memory; returns this thread's sum of squares
+__device__ __forceinline__ float ll_gather(const uint2* buf, int n, uint32_t tag, float* xs) {
+    float ss = 0.f;
+    const int pairs = n >> 1;
+    for (int i0 = threadIdx.x; i0 < pairs; i0 += 4 * NCONS) {      // up to 4 independent 16-byte loads in flight
+        uint4 v[4];
+        bool ok;
+        do {
+            ok = true;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * NCONS;
+                if (i < pairs) { v[u] = ll_load2(buf + 2 * i); ok = ok && (v[u].y == tag) && (v[u].w == tag); }
+            }
+        } while (!ok);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * NCONS;
+            if (i < pairs) {
+                const float a = __uint_as_float(v[u].x), b = __uint_as_float(v[u].z);
+                xs[2 * i] = a; xs[2 * i + 1] = b;
+                ss = fmaf(a, a, ss); ss = fmaf(b, b, ss);
+            }
+        }
     }
-    cons_sync();
+    return ss;
 }
 
 struct Ring {
@@ -110,7 +150,6 @@ __device__ __forceinline__ Slice make_slice(const bf16* W, int N, int K, int rst
     s.rpc &= ~1;                        // keep (gate, up) pairs together
     return s;
 }
-__device__ __forceinline__ int n_chunks(const Slice& s) { return (s.r1 - s.r0 + s.rpc - 1) / s.rpc; }
 
 // producer: issue all chunks of a slice
 __device__ __forceinline__ void produce(const Slice& s, const Ring& ring, uint32_t& q) {
@@ -151,13 +190,16 @@ __device__ __forceinline__ float row_dot(const uint4* wrow, const float (&xr)[K 
 enum { ME_STORE = 0, ME_RESID = 1, ME_SWIGLU = 2, ME_ARGMAX = 3 };
 
 // consumer: process all chunks of a slice.  `xs` holds the (already normalised) activation vector.
+// Results are published as tagged words to `out` (ME_STORE / ME_SWIGLU), added to the CTA-local
+// residual rows `xres` and published (ME_RESID), or folded into the running argmax (ME_ARGMAX).
 template <int K, int EPI>
-__device__ __forceinline__ void consume(const Slice& s, const Ring& ring, uint32_t& q, const float* xs, float* out,
-                                        float& best_v, int& best_i) {
+__device__ __forceinline__ void consume(const Slice& s, const Ring& ring, uint32_t& q, const float* xs, uint2* out,
+                                        uint32_t tag, float* xres, float& best_v, int& best_i) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int RSTEP = (EPI == ME_SWIGLU) ? 2 : 1;
     float xr[K / 32];
     load_xr<K>(xs, xr, lane);
+    cons_sync();                                   // every warp holds its copy: xs may be overwritten from here on
     int unit = 0;                                  // unit index within this CTA's slice
     for (int r = s.r0; r < s.r1; r += s.rpc, ++q) {
         const int rows = min(s.rpc, s.r1 - r);
@@ -172,11 +214,11 @@ __device__ __forceinline__ void consume(const Slice& s, const Ring& ring, uint32
             float v0 = row_dot<K>(base + (size_t)(u * RSTEP) * (K / 8), xr, lane);
             if (EPI == ME_SWIGLU) {
                 float v1 = row_dot<K>(base + (size_t)(u * RSTEP + 1) * (K / 8), xr, lane);
-                if (lane == 0) out[row >> 1] = silu(v0) * v1;
+                if (lane == 0) ll_store(out + (row >> 1), silu(v0) * v1, tag);
             } else if (EPI == ME_STORE) {
-                if (lane == 0) out[row] = v0;
+                if (lane == 0) ll_store(out + row, v0, tag);
             } else if (EPI == ME_RESID) {
-                if (lane == 0) out[row] = __ldcg(out + row) + v0;
+                if (lane == 0) { const float nv = xres[row - s.r0] + v0; xres[row - s.r0] = nv; ll_store(out + row, nv, tag); }
             } else {
                 if (v0 > best_v) { best_v = v0; best_i = row; }
             }
@@ -187,15 +229,11 @@ __device__ __forceinline__ void consume(const Slice& s, const Ring& ring, uint32
     }
 }
 
-// RMSNorm of a global fp32 vector into shared memory (all consumer threads)
-__device__ __forceinline__ void norm_to_smem(const float* __restrict__ x, const float* __restrict__ w, int n, float eps,
-                                             float* xs, float* red) {
+// finish an RMSNorm whose input already sits in xs (per-thread partial sum of squares `ss`)
+__device__ __forceinline__ void norm_in_smem(float ss, const float* __restrict__ w, int n, float eps, float* xs, float* red) {
     const int tid = threadIdx.x;
-    float s = 0.f;
-    for (int i = tid; i < n; i += NCONS) { float v = __ldcg(x + i); xs[i] = v; s = fmaf(v, v, s); }
-    s = warp_sum(s);
-    cons_sync();
-    if ((tid & 31) == 0) red[tid >> 5] = s;
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) red[tid >> 5] = ss;
     cons_sync();
     float tot = 0.f;
 #pragma unroll
@@ -205,12 +243,14 @@ __device__ __forceinline__ void norm_to_smem(const float* __restrict__ x, const 
     cons_sync();
 }
 
-// per-head RMSNorm + RoPE of one 128-vector by one warp (lane holds d = lane, +32, +64, +96)
-__device__ __forceinline__ void head_norm_rope(const float* __restrict__ src, const float* __restrict__ nw, float eps,
-                                               const float* __restrict__ cs, const float* __restrict__ sn, float* dst, int lane) {
+// per-head RMSNorm + RoPE of one 128-vector by one warp (lane holds d = lane, +32, +64, +96);
+// input = tagged words
+__device__ __forceinline__ void head_norm_rope(const uint2* __restrict__ src, uint32_t tag, const float* __restrict__ nw,
+                                               float eps, const float* __restrict__ cs, const float* __restrict__ sn,
+                                               float* dst, int lane) {
     float v[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = __ldcg(src + lane + 32 * i);
+    for (int i = 0; i < 4; ++i) v[i] = ll_poll1(src + lane + 32 * i, tag);
     float ss = warp_sum(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
     const float r = 1.0f / sqrtf(ss / 128.f + eps);
 #pragma unroll
@@ -238,7 +278,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     ring.slots = smem;
     uint8_t* kv_smem = smem + (size_t)NSLOT * SLOT_BYTES;              // [K tile | V tile]
     float* xs = reinterpret_cast<float*>(kv_smem + 2 * KV_TILE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + XS_FLOATS);
+    float* xres = xs + XS_FLOATS;                                      // [XRES_MAX] residual rows owned by this CTA
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xres + XRES_MAX);
     ring.full = bars; ring.empty = bars + NSLOT;
     uint64_t* kv_full = bars + 2 * NSLOT; uint64_t* kv_empty = kv_full + 1;
     float* red = reinterpret_cast<float*>(bars + 2 * NSLOT + 2);      // [64]
@@ -259,7 +300,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     // already in the cache (n_old of them fall in this split), key `pos` is produced in this step.
     const int pos = __ldcg(p.pos);
     const bool att_cta = (int)blockIdx.x < p.nkv * p.nsplit;
-    const int att_g = blockIdx.x / p.nsplit, att_j0 = (blockIdx.x % p.nsplit) * KV_KEYS;
+    const int att_g = blockIdx.x / p.nsplit, att_sp = blockIdx.x % p.nsplit, att_j0 = att_sp * KV_KEYS;
     const int n_old = att_cta ? max(0, min(pos - att_j0, KV_KEYS)) : 0;
     uint32_t kvq = 0;
     uint32_t q = 0;
@@ -270,9 +311,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                 produce(make_slice(w.wqkv, QD + 2 * p.KVD, H, 1), ring, q);
                 if (n_old > 0) {   // K/V rows of earlier positions do not depend on this step: prefetch them too
                     mbar_wait(kv_empty, (kvq & 1) ^ 1);
-                    const uint32_t bytes = (uint32_t)n_old * 128 * 4;
+                    const uint32_t bytes = (uint32_t)n_old * HD * 4;
                     mbar_expect_tx(kv_full, 2 * bytes);
-                    const size_t off = (size_t)l * p.cache_layer_stride + ((size_t)att_g * p.max_ctx + att_j0) * 128;
+                    const size_t off = (size_t)l * p.cache_layer_stride + ((size_t)att_g * p.max_ctx + att_j0) * HD;
                     bulk_g2s(kv_smem, p.kcache + off, bytes, kv_full);
                     bulk_g2s(kv_smem + KV_TILE_BYTES, p.vcache + off, bytes, kv_full);
                     ++kvq;
@@ -290,41 +331,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     long long* dbg_row = nullptr; int dbg_i = 0;
     if (p.dbg && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) dbg_row = p.dbg + (blockIdx.x == 0 ? 0 : DBG_SLOTS);
     MEGA_MARK();
-    const int HD = 128, half = 64;
+    const int half = HD / 2;
     const float* cs = p.rope_cos + (size_t)pos * half;
     const float* sn = p.rope_sin + (size_t)pos * half;
-    unsigned bar_target = 0;
     const unsigned G = gridDim.x;
     float best_v = -INFINITY; int best_i = 0x7fffffff;
-    const int PSTRIDE = HD + 2;
+    // tag = launch epoch (unique per executed step, survives new utterances that revisit the same positions)
+    const uint32_t tag_base = (__ldcg(p.bar + 1) & 0xffffffu) << 8;
+
+    // residual rows owned by this CTA (same row partition for o_proj and down_proj)
+    const Slice xsl = make_slice(nullptr, H, QD, 1);
+    for (int i = tid; i < xsl.r1 - xsl.r0; i += NCONS) xres[i] = __ldcg(p.x + xsl.r0 + i);
 
     for (int l = 0; l < p.L; ++l) {
         const DecLayerW w = p.layers[l];
+        const uint32_t tl = tag_base | ((uint32_t)l << 3);
         // ---- phase 1: RMSNorm + [q|k|v] GEMV ----
-        norm_to_smem(p.x, w.ln_in, H, p.eps, xs, red);
-        consume<H, ME_STORE>(make_slice(w.wqkv, QD + 2 * p.KVD, H, 1), ring, q, xs, p.qkv, best_v, best_i);
-        MEGA_MARK();
-        bar_target += G; grid_sync(p.bar, bar_target);
+        {
+            float ss = 0.f;
+            if (l == 0) { for (int i = tid; i < H; i += NCONS) { const float v = __ldcg(p.x + i); xs[i] = v; ss = fmaf(v, v, ss); } }
+            else ss = ll_gather(p.x_ll, H, (tag_base | ((uint32_t)(l - 1) << 3)) | PH_XD, xs);
+            norm_in_smem(ss, w.ln_in, H, p.eps, xs, red);
+        }
+        consume<H, ME_STORE>(make_slice(w.wqkv, QD + 2 * p.KVD, H, 1), ring, q, xs, p.qkv_ll, tl | PH_QKV, xres, best_v, best_i);
         MEGA_MARK();
         // ---- phase 2: attention partials, work item = (kv head, 64-key split) ----
         {
             const int nk = pos + 1;                              // keys 0..pos
             const int nloc = att_cta ? max(0, min(nk - att_j0, KV_KEYS)) : 0;   // keys of this split incl. the new one
+            const int nact = min(p.nsplit, (pos + KV_KEYS) / KV_KEYS);          // splits holding at least one key
             if (nloc > 0) {
                 const int g = att_g;
                 float* qs = xs;                       // [group][128]
                 float* kn = qs + p.group * HD;        // [128]
                 float* vn = kn + HD;                  // [128]
                 float* sc = vn + HD;                  // [group][KV_KEYS]
-                float* ex = sc + p.group * KV_KEYS;   // [group][128]
+                float* ml = sc + p.group * KV_KEYS;   // [group][2] (max, sum)
                 float* Ks = reinterpret_cast<float*>(kv_smem);
                 float* Vs = reinterpret_cast<float*>(kv_smem + KV_TILE_BYTES);
                 const bool has_new = (pos >= att_j0) && (pos < att_j0 + KV_KEYS);
-                if (warp < p.group) head_norm_rope(p.qkv + (size_t)(g * p.group + warp) * HD, w.qnorm, p.eps, cs, sn, qs + warp * HD, lane);
-                else if (warp == p.group && has_new) head_norm_rope(p.qkv + QD + (size_t)g * HD, w.knorm, p.eps, cs, sn, kn, lane);
+                cons_sync();                          // xs (phase-1 activations) no longer needed by any warp
+                if (warp < p.group) head_norm_rope(p.qkv_ll + (size_t)(g * p.group + warp) * HD, tl | PH_QKV, w.qnorm, p.eps, cs, sn, qs + warp * HD, lane);
+                else if (warp == p.group && has_new) head_norm_rope(p.qkv_ll + QD + (size_t)g * HD, tl | PH_QKV, w.knorm, p.eps, cs, sn, kn, lane);
                 else if (warp == p.group + 1 && has_new) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) vn[lane + 32 * i] = __ldcg(p.qkv + QD + p.KVD + (size_t)g * HD + lane + 32 * i);
+                    for (int i = 0; i < 4; ++i) vn[lane + 32 * i] = ll_poll1(p.qkv_ll + QD + p.KVD + (size_t)g * HD + lane + 32 * i, tl | PH_QKV);
                 }
                 if (n_old > 0) mbar_wait(kv_full, kvq & 1);      // prefetched K/V tiles have landed
                 cons_sync();
@@ -336,13 +387,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                     Ks[(pos - att_j0) * HD + tid] = kx; Vs[(pos - att_j0) * HD + tid] = vx;
                 }
                 cons_sync();
-                const float div = sqrtf((float)HD);
-                for (int j = warp; j < nloc; j += NCONS_WARPS) {
-                    const float4 kv = *reinterpret_cast<const float4*>(Ks + j * HD + lane * 4);
-                    for (int hq = 0; hq < p.group; ++hq) {
-                        const float4 qv = *reinterpret_cast<const float4*>(qs + hq * HD + lane * 4);
-                        float dot = warp_sum(kv.x * qv.x + kv.y * qv.y + kv.z * qv.z + kv.w * qv.w);
-                        if (lane == 0) sc[hq * KV_KEYS + j] = dot / div;
+                // scores: one thread per (head, key); the d loop is rotated by the key index so that the
+                // 32 lanes of a warp hit 32 different banks of the row-major K tile
+                for (int idx = tid; idx < p.group * KV_KEYS; idx += NCONS) {
+                    const int hq = idx / KV_KEYS, j = idx - hq * KV_KEYS;
+                    if (j < nloc) {
+                        const float* kr = Ks + j * HD; const float* qr = qs + hq * HD;
+                        float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+                        for (int dd = 0; dd < HD; dd += 2) {
+                            const int d0 = (dd + j) & (HD - 1), d1 = (dd + 1 + j) & (HD - 1);
+                            a0 = fmaf(kr[d0], qr[d0], a0); a1 = fmaf(kr[d1], qr[d1], a1);
+                        }
+                        sc[hq * KV_KEYS + j] = (a0 + a1) / sqrtf((float)HD);
                     }
                 }
                 cons_sync();
@@ -356,27 +413,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                         sc[warp * KV_KEYS + j] = e; sum += e;
                     }
                     sum = warp_sum(sum);
-                    if (lane == 0) {
-                        float* pp = p.attn_part + ((size_t)blockIdx.x * p.group + warp) * PSTRIDE;
-                        pp[HD] = mx; pp[HD + 1] = sum;
-                    }
+                    if (lane == 0) { ml[warp * 2] = mx; ml[warp * 2 + 1] = sum; }
                 }
                 cons_sync();
-                {   // o[hq][d] = sum_j e[hq][j] * V[j][d]; thread = (d, key-parity partition)
-                    const int d = tid & (HD - 1), part = tid >> 7;
-                    float acc[8];
-#pragma unroll
-                    for (int hq = 0; hq < 8; ++hq) acc[hq] = 0.f;
-                    for (int j = part; j < nloc; j += 2) {
-                        const float vv = Vs[j * HD + d];
-#pragma unroll
-                        for (int hq = 0; hq < 8; ++hq) if (hq < p.group) acc[hq] = fmaf(sc[hq * KV_KEYS + j], vv, acc[hq]);
-                    }
-                    if (part == 1) for (int hq = 0; hq < p.group; ++hq) ex[hq * HD + d] = acc[hq];
-                    cons_sync();
-                    if (part == 0)
-                        for (int hq = 0; hq < p.group; ++hq)
-                            p.attn_part[((size_t)blockIdx.x * p.group + hq) * PSTRIDE + d] = acc[hq] + ex[hq * HD + d];
+                // o[hq][d] = sum_j e[hq][j] * V[j][d]; thread = (head, d); publish the partial record
+                for (int idx = tid; idx < p.group * HD; idx += NCONS) {
+                    const int hq = idx / HD, d = idx - hq * HD;
+                    float acc = 0.f;
+                    for (int j = 0; j < nloc; ++j) acc = fmaf(sc[hq * KV_KEYS + j], Vs[j * HD + d], acc);
+                    uint2* rec = p.part_ll + ((size_t)blockIdx.x * p.group + hq) * PSTRIDE;
+                    ll_store(rec + d, acc, tl | PH_PART);
+                    if (d < 2) ll_store(rec + HD + d, ml[hq * 2 + d], tl | PH_PART);
                 }
                 if (n_old > 0) {                      // hand the K/V staging buffer back to the producer
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -384,51 +431,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                     if (lane == 0) mbar_arrive(kv_empty);
                     ++kvq;
                 }
-            }
-        }
-        MEGA_MARK();
-        bar_target += G; grid_sync(p.bar, bar_target);
-        MEGA_MARK();
-        // ---- phase 3: merge attention partials -> o_proj GEMV + residual ----
-        {
-            const int nact = min(p.nsplit, (pos + KV_KEYS) / KV_KEYS);     // splits holding at least one of keys 0..pos
-            for (int o = tid; o < QD; o += NCONS) {
-                const int h = o / HD, d = o - h * HD;
-                const int g = h / p.group, hq = h - g * p.group;
-                float M = -INFINITY;
-                for (int s2 = 0; s2 < nact; ++s2) M = fmaxf(M, __ldcg(p.attn_part + ((size_t)(g * p.nsplit + s2) * p.group + hq) * PSTRIDE + HD));
-                float Lsum = 0.f, O = 0.f;
-                for (int s2 = 0; s2 < nact; ++s2) {
-                    const float* pp = p.attn_part + ((size_t)(g * p.nsplit + s2) * p.group + hq) * PSTRIDE;
-                    const float sc_ = expf(__ldcg(pp + HD) - M);
-                    Lsum = fmaf(__ldcg(pp + HD + 1), sc_, Lsum);
-                    O = fmaf(__ldcg(pp + d), sc_, O);
+                // split 0 of every kv head merges the partials of all active splits and publishes the head outputs
+                if (att_sp == 0) {
+                    for (int idx = tid; idx < p.group * HD; idx += NCONS) {
+                        const int hq = idx / HD, d = idx - hq * HD;
+                        float M = -INFINITY, Lsum = 0.f, O = 0.f;
+                        for (int s2 = 0; s2 < nact; ++s2) {
+                            const uint2* rec = p.part_ll + ((size_t)(g * p.nsplit + s2) * p.group + hq) * PSTRIDE;
+                            const float ms = ll_poll1(rec + HD, tl | PH_PART), ls = ll_poll1(rec + HD + 1, tl | PH_PART);
+                            const float os = ll_poll1(rec + d, tl | PH_PART);
+                            const float Mn = fmaxf(M, ms);
+                            const float a = expf(M - Mn), b = expf(ms - Mn);     // exp(-inf) = 0 on the first split
+                            Lsum = Lsum * a + ls * b; O = O * a + os * b; M = Mn;
+                        }
+                        ll_store(p.attn_ll + (size_t)(g * p.group + hq) * HD + d, O / Lsum, tl | PH_ATTN);
+                    }
                 }
-                xs[o] = O / Lsum;
+                cons_sync();                          // attention scratch (aliases xs) is free again
             }
         }
-        cons_sync();
-        consume<QD, ME_RESID>(make_slice(w.wo, H, QD, 1), ring, q, xs, p.x, best_v, best_i);
         MEGA_MARK();
-        bar_target += G; grid_sync(p.bar, bar_target);
+        // ---- phase 3: o_proj GEMV + residual ----
+        ll_gather(p.attn_ll, QD, tl | PH_ATTN, xs);
+        cons_sync();
+        consume<QD, ME_RESID>(make_slice(w.wo, H, QD, 1), ring, q, xs, p.x_ll, tl | PH_XO, xres, best_v, best_i);
         MEGA_MARK();
         // ---- phase 4: RMSNorm + gate/up GEMV + SiLU*mul ----
-        norm_to_smem(p.x, w.ln_post, H, p.eps, xs, red);
-        consume<H, ME_SWIGLU>(make_slice(w.wgu, 2 * I, H, 2), ring, q, xs, p.act, best_v, best_i);
-        MEGA_MARK();
-        bar_target += G; grid_sync(p.bar, bar_target);
+        cons_sync();
+        {
+            const float ss = ll_gather(p.x_ll, H, tl | PH_XO, xs);
+            norm_in_smem(ss, w.ln_post, H, p.eps, xs, red);
+        }
+        consume<H, ME_SWIGLU>(make_slice(w.wgu, 2 * I, H, 2), ring, q, xs, p.act_ll, tl | PH_ACT, xres, best_v, best_i);
         MEGA_MARK();
         // ---- phase 5: down GEMV + residual ----
-        for (int i = tid; i < I; i += NCONS) xs[i] = __ldcg(p.act + i);
         cons_sync();
-        consume<I, ME_RESID>(make_slice(w.wdown, H, I, 1), ring, q, xs, p.x, best_v, best_i);
+        ll_gather(p.act_ll, I, tl | PH_ACT, xs);
+        cons_sync();
+        consume<I, ME_RESID>(make_slice(w.wdown, H, I, 1), ring, q, xs, p.x_ll, tl | PH_XD, xres, best_v, best_i);
         MEGA_MARK();
-        bar_target += G; grid_sync(p.bar, bar_target);
-        MEGA_MARK();
+        cons_sync();
     }
     // ---- final RMSNorm + tied lm_head GEMV + argmax ----
-    norm_to_smem(p.x, p.final_norm, H, p.eps, xs, red);
-    consume<H, ME_ARGMAX>(make_slice(p.lm_head, p.V, H, 1), ring, q, xs, nullptr, best_v, best_i);
+    {
+        const float ss = ll_gather(p.x_ll, H, (tag_base | ((uint32_t)(p.L - 1) << 3)) | PH_XD, xs);
+        norm_in_smem(ss, p.final_norm, H, p.eps, xs, red);
+    }
+    consume<H, ME_ARGMAX>(make_slice(p.lm_head, p.V, H, 1), ring, q, xs, nullptr, 0u, xres, best_v, best_i);
     MEGA_MARK();
     // every lane of a warp saw the same values: lane 0 publishes the warp's best
     cons_sync();
@@ -441,7 +490,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
             if (red[wq] > v || (red[wq] == v && ired[wq] < idx)) { v = red[wq]; idx = ired[wq]; }
         p.part_val[blockIdx.x] = v; p.part_idx[blockIdx.x] = idx;
         __threadfence();
-        unsigned t = atomicAdd(p.bar + 1, 1u);
+        unsigned t = atomicAdd(p.bar, 1u);
         is_last = (t == G - 1);
     }
     cons_sync();
@@ -470,7 +519,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
             if (tok == 151643 || tok == 151645 || n >= p.max_new) { *p.done = 1; *p.next_id = -1; tok = -1; }
             else { p.ids_out[n] = tok; *p.n_out = n + 1; *p.pos = pos + 1; *p.next_id = tok; }
             tok_s = tok;
-            p.bar[0] = 0; p.bar[1] = 0;          // all CTAs are past every barrier: reset for the next launch
+            p.bar[0] = 0;                        // every CTA has taken its ticket: reset for the next launch
+            p.bar[1] = p.bar[1] + 1;             // new epoch: words published by this step can never match again
         }
         cons_sync();
         const int tok = tok_s;
@@ -484,15 +534,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
 }  // namespace mega
 
 // host side ---------------------------------------------------------------------------------------
-struct MegaState {
-    DecLayerW* d_layers = nullptr; unsigned* d_bar = nullptr; float* d_part = nullptr; long long* d_dbg = nullptr;
-    int part_cap = 0; const Model* model = nullptr;
-};
-static MegaState g_mega;   // one model per process in practice; re-created when the model changes
+static long long* g_last_dbg = nullptr;   // debug only (ASRB_MEGA_DEBUG): timeline buffer of the last launch
 
 static size_t mega_smem_bytes() {
-    return (size_t)mega::NSLOT * mega::SLOT_BYTES + 2 * mega::KV_TILE_BYTES + mega::XS_FLOATS * 4 + (2 * mega::NSLOT + 2) * 8 +
-           64 * 4 + 64 * 4 + 64;
+    return (size_t)mega::NSLOT * mega::SLOT_BYTES + 2 * mega::KV_TILE_BYTES + (mega::XS_FLOATS + mega::XRES_MAX) * 4 +
+           (2 * mega::NSLOT + 2) * 8 + 64 * 4 + 64 * 4 + 64;
 }
 
 template <int H, int QD, int I> static bool dims_match(const asrb_dims& c) {
@@ -504,51 +550,51 @@ bool decode_mega_supported(const Model& m, int B, int max_ctx) {
     if (B != 1 || c.head_dim != 128) return false;
     const int group = c.num_attention_heads / c.num_key_value_heads;
     if (group + 2 > mega::NCONS_WARPS) return false;
-    if ((size_t)(group * 128 + 256 + group * mega::KV_KEYS + group * 128) > (size_t)mega::XS_FLOATS) return false;
+    if ((size_t)(group * 128 + 256 + group * mega::KV_KEYS + group * 2) > (size_t)mega::XS_FLOATS) return false;
     if (m.ctx->smem_optin < mega_smem_bytes()) return false;
+    if ((c.hidden_size + m.ctx->sm_count - 1) / m.ctx->sm_count + 1 > mega::XRES_MAX) return false;
+    if (c.num_hidden_layers > 32) return false;                  // 5-bit layer field
     if (((max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS) * c.num_key_value_heads > m.ctx->sm_count) return false;   // one CTA per (kv head, 64-key split)
     return dims_match<1024, 2048, 3072>(c) || dims_match<256, 512, 512>(c);
 }
 
+// floats of session scratch the fused step needs: tagged exchange buffers (2 floats per value)
+size_t decode_mega_part_floats(const Model& m) {
+    const asrb_dims& c = m.d.c;
+    const int group = c.num_attention_heads / c.num_key_value_heads;
+    const size_t words = (size_t)m.d.qkv_dim + (size_t)m.ctx->sm_count * group * mega::PSTRIDE + m.d.q_dim + c.hidden_size +
+                         c.intermediate_size + 64;
+    return 2 * words;
+}
+
 void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* kcache, float* vcache,
-                             size_t cache_layer_stride, size_t cache_seq_stride, int max_ctx, cudaStream_t st,
-                             int64_t* launches) {
+                             size_t cache_layer_stride, size_t cache_seq_stride, int max_ctx, const MegaBufs& mb,
+                             cudaStream_t st, int64_t* launches) {
     (void)cache_seq_stride;
     ASRB_REQUIRE(decode_mega_supported(m, B, max_ctx), ASRB_ERR_STATE, "fused decode step not supported for this model/batch");
+    ASRB_REQUIRE(m.d_dec_layers && mb.bar && mb.part, ASRB_ERR_STATE, "fused decode step buffers missing");
     const asrb_dims& c = m.d.c;
     const int G = m.ctx->sm_count;
     const int group = c.num_attention_heads / c.num_key_value_heads;
     const int nsplit = (max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS;
-    ASRB_REQUIRE(nsplit * c.num_key_value_heads <= G, ASRB_ERR_INVALID, "context too long for the fused decode step");
-    if (g_mega.model != &m) {
-        if (g_mega.d_layers) { cudaFree(g_mega.d_layers); cudaFree(g_mega.d_bar); g_mega.d_layers = nullptr; }
-        ASRB_CUDA_CHECK(cudaMalloc(&g_mega.d_layers, m.dec.size() * sizeof(DecLayerW)));
-        ASRB_CUDA_CHECK(cudaMemcpy(g_mega.d_layers, m.dec.data(), m.dec.size() * sizeof(DecLayerW), cudaMemcpyHostToDevice));
-        ASRB_CUDA_CHECK(cudaMalloc(&g_mega.d_bar, 4 * sizeof(unsigned)));
-        ASRB_CUDA_CHECK(cudaMemset(g_mega.d_bar, 0, 4 * sizeof(unsigned)));
-        g_mega.model = &m;
-    }
-    const int need_part = G * group * (128 + 2);
-    if (g_mega.part_cap < need_part) {
-        if (g_mega.d_part) cudaFree(g_mega.d_part);
-        ASRB_CUDA_CHECK(cudaMalloc(&g_mega.d_part, (size_t)need_part * sizeof(float)));
-        g_mega.part_cap = need_part;
-    }
     mega::Params p{};
-    p.layers = g_mega.d_layers; p.lm_head = m.lm_head; p.embed = m.embed; p.final_norm = m.final_norm;
+    p.layers = m.d_dec_layers; p.lm_head = m.lm_head; p.embed = m.embed; p.final_norm = m.final_norm;
     p.rope_cos = m.rope_cos; p.rope_sin = m.rope_sin; p.eps = (float)c.rms_norm_eps;
     p.L = c.num_hidden_layers; p.H = c.hidden_size; p.QD = m.d.q_dim; p.KVD = m.d.kv_dim; p.I = c.intermediate_size;
     p.V = c.vocab_size; p.nq = c.num_attention_heads; p.nkv = c.num_key_value_heads; p.group = group;
-    p.x = b.x; p.qkv = b.qkv; p.act = b.act; p.attn_part = g_mega.d_part;
+    p.x = b.x;
     p.kcache = kcache; p.vcache = vcache; p.cache_layer_stride = cache_layer_stride; p.max_ctx = max_ctx; p.nsplit = nsplit;
     p.part_val = b.part_val; p.part_idx = b.part_idx;
     p.pos = b.pos; p.done = b.done; p.next_id = b.next_id; p.ids_out = b.ids_out; p.n_out = b.n_out; p.max_new = b.max_new;
-    p.bar = g_mega.d_bar;
-    if (getenv("ASRB_MEGA_DEBUG")) {
-        if (!g_mega.d_dbg) { ASRB_CUDA_CHECK(cudaMalloc(&g_mega.d_dbg, 2 * mega::DBG_SLOTS * sizeof(long long)));
-                             ASRB_CUDA_CHECK(cudaMemset(g_mega.d_dbg, 0, 2 * mega::DBG_SLOTS * sizeof(long long))); }
-        p.dbg = g_mega.d_dbg;
-    }
+    p.bar = mb.bar;
+    uint2* w = reinterpret_cast<uint2*>(mb.part);            // 16-byte aligned sub-buffers (even word counts)
+    p.qkv_ll = w; w += m.d.qkv_dim;
+    p.part_ll = w; w += (size_t)G * group * mega::PSTRIDE;
+    p.attn_ll = w; w += m.d.q_dim;
+    p.x_ll = w; w += c.hidden_size;
+    p.act_ll = w;
+    p.dbg = mb.dbg;
+    g_last_dbg = mb.dbg;
     const size_t smem = mega_smem_bytes();
     void* args[] = {(void*)&p};
     const void* fn = nullptr;
@@ -561,10 +607,11 @@ void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* 
 
 // debug: copy the clock64 timeline of the most recent fused step (CTA 0 then CTA G-1), returns slots per CTA
 int decode_mega_debug_timeline(long long* out, int cap) {
-    if (!g_mega.d_dbg || cap < 2 * mega::DBG_SLOTS) return 0;
+    if (!g_last_dbg || cap < 2 * mega::DBG_SLOTS) return 0;
     cudaDeviceSynchronize();
-    cudaMemcpy(out, g_mega.d_dbg, 2 * mega::DBG_SLOTS * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(out, g_last_dbg, 2 * mega::DBG_SLOTS * sizeof(long long), cudaMemcpyDeviceToHost);
     return mega::DBG_SLOTS;
 }
+int decode_mega_dbg_slots() { return 2 * mega::DBG_SLOTS; }
 
 }  // namespace asrb

@@ -71,6 +71,7 @@ struct Model {
     bf16 *embed = nullptr, *lm_head = nullptr;
     std::vector<DecLayerW> dec;
     float* final_norm = nullptr;
+    DecLayerW* d_dec_layers = nullptr;   // device copy of `dec` (pointer table read by the fused decode step)
     float *rope_cos = nullptr, *rope_sin = nullptr;   // [rope_max_pos][head_dim/2]
     int rope_max_pos = 0;
 
@@ -172,6 +173,9 @@ void launch_decode_step_phases(const Model& m, const DecodeBufs& b, int B, float
                                bool write_logits, cudaStream_t st, int64_t* launches);
 // final-norm + lm_head + argmax on arbitrary rows of a residual stream (prefill last rows);
 // also performs the greedy bookkeeping of src/inference.rs:161-170 (EOS check, append, embed)
+struct MegaBufs { unsigned* bar = nullptr; float* part = nullptr; long long* dbg = nullptr; };   // per-session state of the fused step
+size_t decode_mega_part_floats(const Model& m);
+int decode_mega_dbg_slots();
 void launch_greedy(const Model& m, const DecodeBufs& b, int B, cudaStream_t st, int64_t* launches);
 void launch_lmhead_argmax(const Model& m, const float* x_rows, const int* d_row_idx, int B,
                           const DecodeBufs& b, bool write_logits, cudaStream_t st, int64_t* launches);

@@ -316,6 +316,8 @@ void model_finalize(Model* m) {
         drop_raw(m, p + ".mlp.gate_proj.weight"); drop_raw(m, p + ".mlp.up_proj.weight");
         w.wdown = take<bf16>(m, p + ".mlp.down_proj.weight", {H, I}, true);
     }
+    m->d_dec_layers = dev_alloc<DecLayerW>(m, m->dec.size());
+    ASRB_CUDA_CHECK(cudaMemcpy(m->d_dec_layers, m->dec.data(), m->dec.size() * sizeof(DecLayerW), cudaMemcpyHostToDevice));
     build_mel_tables(m);
     build_pos_tables(m);
     ASRB_CUDA_CHECK(cudaDeviceSynchronize());

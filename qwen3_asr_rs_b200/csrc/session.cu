@@ -46,6 +46,7 @@ struct Session {
     bf16 *dh = nullptr, *dattn = nullptr, *dact = nullptr; size_t dh_ps = 0, dattn_ps = 0, dact_ps = 0;
     float *kcache = nullptr, *vcache = nullptr; size_t cache_layer_stride = 0, cache_seq_stride = 0;
     DecodeBufs db{};
+    MegaBufs mega{};
     int* d_lastrow = nullptr;
     int *h_done = nullptr, *h_ids = nullptr, *h_nout = nullptr, *h_next = nullptr;
     // int-plan offsets (into d_int)
@@ -156,6 +157,10 @@ Session* session_create(Model* m, int max_batch, int64_t max_samples, int max_la
         b.ids_out = salloc<int>(s, Bm * max_new); b.n_out = salloc<int>(s, Bm);
         b.max_new = max_new;
         s->d_lastrow = salloc<int>(s, Bm);
+        s->mega.bar = salloc<unsigned>(s, 4, true);
+        { const unsigned one = 1; ASRB_CUDA_CHECK(cudaMemcpy(s->mega.bar + 1, &one, sizeof(one), cudaMemcpyHostToDevice)); }   // epoch 1
+        s->mega.part = salloc<float>(s, decode_mega_part_floats(*m), true);   // zero = tag 0 = never written
+        if (getenv("ASRB_MEGA_DEBUG")) s->mega.dbg = salloc<long long>(s, decode_mega_dbg_slots(), true);
         ASRB_CUDA_CHECK(cudaMallocHost(&s->h_done, Bm * sizeof(int)));
         ASRB_CUDA_CHECK(cudaMallocHost(&s->h_nout, Bm * sizeof(int)));
         ASRB_CUDA_CHECK(cudaMallocHost(&s->h_next, Bm * sizeof(int)));
@@ -421,8 +426,10 @@ void session_prefill(Session* s, const int64_t* const* lang_ids, const int32_t* 
 // -------------------------------------------------------------------------------------------------
 bool decode_mega_supported(const Model& m, int B, int max_ctx);
 void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* kcache, float* vcache,
-                             size_t cache_layer_stride, size_t cache_seq_stride, int max_ctx, cudaStream_t st,
-                             int64_t* launches);
+                             size_t cache_layer_stride, size_t cache_seq_stride, int max_ctx, const MegaBufs& mb,
+                             cudaStream_t st, int64_t* launches);
+size_t decode_mega_part_floats(const Model& m);
+int decode_mega_dbg_slots();
 
 // one iteration of the loop body: decoder forward on the pending token, then the greedy bookkeeping
 // that selects / appends / embeds the next one.  (The fused kernel does both.)
@@ -433,7 +440,7 @@ static void forward_step(Session* s, bool write_logits) {
     Model& m = *s->m;
     if (use_mega(s, write_logits)) {
         launch_decode_step_mega(m, s->db, s->B, s->kcache, s->vcache, s->cache_layer_stride, s->cache_seq_stride, s->max_ctx,
-                                s->st, &s->launches);
+                                s->mega, s->st, &s->launches);
     } else {
         launch_decode_step_phases(m, s->db, s->B, s->kcache, s->vcache, s->cache_layer_stride, s->cache_seq_stride, s->max_ctx,
                                   write_logits, s->st, &s->launches);

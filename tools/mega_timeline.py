@@ -20,12 +20,13 @@ buf = (C.c_longlong * 1024)()
 n = lib.asrb_debug_mega_timeline(buf, 1024)
 t = np.array(buf[:], dtype=np.int64).reshape(2, -1)
 L = cfg.text.num_hidden_layers
-names = ["p1_qkv", "bar1", "p2_attn", "bar2", "p3_oproj", "bar3", "p4_gateup", "bar4", "p5_down", "bar5"]
+names = ["p1_qkv", "p2_attn", "p3_oproj", "p4_gateup", "p5_down"]   # each includes the wait for its inputs
+NP = len(names)
 for cta, row in zip(("cta0", "ctaLast"), t):
-    marks = row[: 2 + 10 * L]
+    marks = row[: 2 + NP * L]
     d = np.diff(marks)
-    per = d[: 10 * L].reshape(L, 10)
-    print(cta, "total cycles", int(marks[-1] - marks[0]), " lm_head cycles", int(d[10 * L]))
+    per = d[: NP * L].reshape(L, NP)
+    print(cta, "total cycles", int(marks[-1] - marks[0]), " lm_head cycles", int(d[NP * L]))
     print("  mean cycles per phase over layers:")
     for i, nm in enumerate(names):
         print(f"    {nm:10s} mean {per[:, i].mean():9.0f}  min {per[:, i].min():7d}  max {per[:, i].max():7d}")
