@@ -115,8 +115,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_kernel(AttnParams p) {
     }
 }
 
+bool launch_attention_tc(const AttnParams& p, int hd, cudaStream_t st);   // attention_tc.cu
+
 void launch_attention(const AttnParams& p, int hd, cudaStream_t st) {
     if (p.nseg <= 0 || p.max_len <= 0) return;
+    static const bool force_simt = [] { const char* e = getenv("ASRB_ATTN"); return e && std::string(e) == "simt"; }();
+    if (!force_simt && launch_attention_tc(p, hd, st)) return;
     dim3 grid((p.max_len + QT - 1) / QT, p.nheads, p.nseg);
     if (hd == 64) {
         size_t smem = (QT * 65 + KT * 65 + KT * 64 + QT * KT) * sizeof(float);

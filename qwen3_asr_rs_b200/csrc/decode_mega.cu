@@ -107,6 +107,19 @@ __device__ __forceinline__ float ll_poll1(const uint2* p, uint32_t tag) {
     } while (v.y != tag);
     return __uint_as_float(v.x);
 }
+// four words at p, p+stride, ... : all loads are issued before any tag is examined (one round trip when ready)
+__device__ __forceinline__ void ll_poll4(const uint2* p, int stride, uint32_t tag, float (&out)[4]) {
+    uint2 v[4];
+    bool ok;
+    do {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v[i].x), "=r"(v[i].y) : "l"(p + (size_t)i * stride) : "memory");
+        ok = (v[0].y == tag) && (v[1].y == tag) && (v[2].y == tag) && (v[3].y == tag);
+    } while (!ok);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = __uint_as_float(v[i].x);
+}
 // all consumer threads: gather n (even) tagged values into shared memory; returns this thread's sum of squares
 __device__ __forceinline__ float ll_gather(const uint2* buf, int n, uint32_t tag, float* xs) {
     float ss = 0.f;
@@ -151,8 +164,45 @@ __device__ __forceinline__ Slice make_slice(const bf16* W, int N, int K, int rst
     return s;
 }
 
-// producer: issue all chunks of a slice
-__device__ __forceinline__ void produce(const Slice& s, const Ring& ring, uint32_t& q) {
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+// The shared-memory ring only buffers ~2.7 us of the weight stream (120 KB at this SM's 44 GB/s share of
+// HBM) while the consumers' dependency stalls last tens of us per layer.  So the producer also runs an
+// L2 prefetch cursor PF_AHEAD chunks (~1.5 layers, ~57 MB chip-wide of the 126 MB L2) ahead of the ring:
+// HBM streams continuously into L2, and the ring refills from L2 at low latency.
+static constexpr int PF_AHEAD = 16;
+template <int H, int QD, int I>
+struct ChunkCursor {
+    int l, ph, r; Slice s; bool done;
+    __device__ void load(const Params& p) {
+        if (l >= p.L) { if (l == p.L && ph == 0) s = make_slice(p.lm_head, p.V, H, 1); else { done = true; return; } }
+        else {
+            const DecLayerW w = p.layers[l];
+            s = ph == 0 ? make_slice(w.wqkv, QD + 2 * p.KVD, H, 1) : ph == 1 ? make_slice(w.wo, H, QD, 1)
+              : ph == 2 ? make_slice(w.wgu, 2 * I, H, 2) : make_slice(w.wdown, H, I, 1);
+        }
+        r = s.r0;
+    }
+    __device__ void init(const Params& p) { l = 0; ph = 0; done = false; load(p); }
+    __device__ bool next(const Params& p, const bf16*& src, uint32_t& bytes) {
+        while (!done && r >= s.r1) {
+            if (l >= p.L) { done = true; break; }
+            if (++ph == 4) { ph = 0; ++l; }
+            load(p);
+        }
+        if (done) return false;
+        const int rows = min(s.rpc, s.r1 - r);
+        src = s.W + (size_t)r * s.K; bytes = (uint32_t)rows * s.K * 2;
+        r += s.rpc;
+        return true;
+    }
+};
+
+// producer: issue all chunks of a slice into the ring; every issued chunk advances the L2 prefetch cursor
+template <class Cursor>
+__device__ __forceinline__ void produce(const Slice& s, const Ring& ring, uint32_t& q, Cursor& pf, const Params& p) {
     for (int r = s.r0; r < s.r1; r += s.rpc, ++q) {
         int rows = min(s.rpc, s.r1 - r);
         uint32_t slot = q % NSLOT, par = (q / NSLOT) & 1;
@@ -160,6 +210,8 @@ __device__ __forceinline__ void produce(const Slice& s, const Ring& ring, uint32
         uint32_t bytes = (uint32_t)rows * s.K * 2;
         mbar_expect_tx(&ring.full[slot], bytes);
         bulk_g2s(ring.slots + (size_t)slot * SLOT_BYTES, s.W + (size_t)r * s.K, bytes, &ring.full[slot]);
+        const bf16* psrc; uint32_t pbytes;
+        if (pf.next(p, psrc, pbytes)) l2_prefetch(psrc, pbytes);
     }
 }
 
@@ -187,6 +239,23 @@ __device__ __forceinline__ float row_dot(const uint4* wrow, const float (&xr)[K 
     return warp_sum(a0 + a1);
 }
 
+// same contraction with the activation vector read from shared memory (long K: keeps registers free)
+template <int K>
+__device__ __forceinline__ float row_dot_smem(const uint4* wrow, const float* xs, int lane) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < K / 256; ++c) {
+        const uint4 w = wrow[c * 32 + lane];
+        const float4 xa = *reinterpret_cast<const float4*>(xs + (c * 32 + lane) * 8);
+        const float4 xb = *reinterpret_cast<const float4*>(xs + (c * 32 + lane) * 8 + 4);
+        a0 = fmaf(bf16_lo(w.x), xa.x, a0); a1 = fmaf(bf16_hi(w.x), xa.y, a1);
+        a0 = fmaf(bf16_lo(w.y), xa.z, a0); a1 = fmaf(bf16_hi(w.y), xa.w, a1);
+        a0 = fmaf(bf16_lo(w.z), xb.x, a0); a1 = fmaf(bf16_hi(w.z), xb.y, a1);
+        a0 = fmaf(bf16_lo(w.w), xb.z, a0); a1 = fmaf(bf16_hi(w.w), xb.w, a1);
+    }
+    return warp_sum(a0 + a1);
+}
+
 enum { ME_STORE = 0, ME_RESID = 1, ME_SWIGLU = 2, ME_ARGMAX = 3 };
 
 // consumer: process all chunks of a slice.  `xs` holds the (already normalised) activation vector.
@@ -197,9 +266,12 @@ __device__ __forceinline__ void consume(const Slice& s, const Ring& ring, uint32
                                         uint32_t tag, float* xres, float& best_v, int& best_i) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int RSTEP = (EPI == ME_SWIGLU) ? 2 : 1;
-    float xr[K / 32];
-    load_xr<K>(xs, xr, lane);
-    cons_sync();                                   // every warp holds its copy: xs may be overwritten from here on
+    constexpr bool XREG = K <= 2048;               // long-K slices (down_proj, 7 rows per CTA) read x from smem instead
+    float xr[XREG ? K / 32 : 1];
+    if (XREG) {
+        load_xr<XREG ? K : 256>(xs, reinterpret_cast<float (&)[(XREG ? K : 256) / 32]>(xr), lane);
+        cons_sync();                               // every warp holds its copy: xs may be overwritten from here on
+    }
     int unit = 0;                                  // unit index within this CTA's slice
     for (int r = s.r0; r < s.r1; r += s.rpc, ++q) {
         const int rows = min(s.rpc, s.r1 - r);
@@ -211,9 +283,12 @@ __device__ __forceinline__ void consume(const Slice& s, const Ring& ring, uint32
         int first = (warp - (unit % NCONS_WARPS) + NCONS_WARPS) % NCONS_WARPS;
         for (int u = first; u < units_here; u += NCONS_WARPS) {
             const int row = r + u * RSTEP;
-            float v0 = row_dot<K>(base + (size_t)(u * RSTEP) * (K / 8), xr, lane);
+            float v0, v1 = 0.f;
+            if (XREG) v0 = row_dot<XREG ? K : 256>(base + (size_t)(u * RSTEP) * (K / 8), reinterpret_cast<const float (&)[(XREG ? K : 256) / 32]>(xr), lane);
+            else v0 = row_dot_smem<K>(base + (size_t)(u * RSTEP) * (K / 8), xs, lane);
             if (EPI == ME_SWIGLU) {
-                float v1 = row_dot<K>(base + (size_t)(u * RSTEP + 1) * (K / 8), xr, lane);
+                if (XREG) v1 = row_dot<XREG ? K : 256>(base + (size_t)(u * RSTEP + 1) * (K / 8), reinterpret_cast<const float (&)[(XREG ? K : 256) / 32]>(xr), lane);
+                else v1 = row_dot_smem<K>(base + (size_t)(u * RSTEP + 1) * (K / 8), xs, lane);
                 if (lane == 0) ll_store(out + (row >> 1), silu(v0) * v1, tag);
             } else if (EPI == ME_STORE) {
                 if (lane == 0) ll_store(out + row, v0, tag);
@@ -227,6 +302,7 @@ __device__ __forceinline__ void consume(const Slice& s, const Ring& ring, uint32
         __syncwarp();
         if (lane == 0) mbar_arrive(&ring.empty[slot]);
     }
+    if (!XREG) cons_sync();                        // xs was read in place: nobody may overwrite it before this point
 }
 
 // finish an RMSNorm whose input already sits in xs (per-thread partial sum of squares `ss`)
@@ -249,8 +325,7 @@ __device__ __forceinline__ void head_norm_rope(const uint2* __restrict__ src, ui
                                                float eps, const float* __restrict__ cs, const float* __restrict__ sn,
                                                float* dst, int lane) {
     float v[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = ll_poll1(src + lane + 32 * i, tag);
+    ll_poll4(src + lane, 32, tag, v);
     float ss = warp_sum(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
     const float r = 1.0f / sqrtf(ss / 128.f + eps);
 #pragma unroll
@@ -306,23 +381,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     uint32_t q = 0;
     if (is_producer) {
         if (lane == 0) {
+            ChunkCursor<H, QD, I> pf;
+            pf.init(p);
+            {   // start the HBM stream immediately: the first PF_AHEAD chunks go to L2 now
+                const bf16* psrc; uint32_t pbytes;
+                for (int i = 0; i < PF_AHEAD; ++i) if (pf.next(p, psrc, pbytes)) l2_prefetch(psrc, pbytes);
+            }
+            const size_t kv_row = ((size_t)att_g * p.max_ctx + att_j0) * HD;
+            if (n_old > 0) {   // K/V tiles of the first two layers
+                l2_prefetch(p.kcache + kv_row, (uint32_t)n_old * HD * 4);
+                l2_prefetch(p.vcache + kv_row, (uint32_t)n_old * HD * 4);
+            }
             for (int l = 0; l < p.L; ++l) {
                 const DecLayerW w = p.layers[l];
-                produce(make_slice(w.wqkv, QD + 2 * p.KVD, H, 1), ring, q);
+                produce(make_slice(w.wqkv, QD + 2 * p.KVD, H, 1), ring, q, pf, p);
                 if (n_old > 0) {   // K/V rows of earlier positions do not depend on this step: prefetch them too
-                    mbar_wait(kv_empty, (kvq & 1) ^ 1);
                     const uint32_t bytes = (uint32_t)n_old * HD * 4;
+                    if (l + 1 < p.L) {
+                        l2_prefetch(p.kcache + (size_t)(l + 1) * p.cache_layer_stride + kv_row, bytes);
+                        l2_prefetch(p.vcache + (size_t)(l + 1) * p.cache_layer_stride + kv_row, bytes);
+                    }
+                    mbar_wait(kv_empty, (kvq & 1) ^ 1);
                     mbar_expect_tx(kv_full, 2 * bytes);
-                    const size_t off = (size_t)l * p.cache_layer_stride + ((size_t)att_g * p.max_ctx + att_j0) * HD;
+                    const size_t off = (size_t)l * p.cache_layer_stride + kv_row;
                     bulk_g2s(kv_smem, p.kcache + off, bytes, kv_full);
                     bulk_g2s(kv_smem + KV_TILE_BYTES, p.vcache + off, bytes, kv_full);
                     ++kvq;
                 }
-                produce(make_slice(w.wo, H, QD, 1), ring, q);
-                produce(make_slice(w.wgu, 2 * I, H, 2), ring, q);
-                produce(make_slice(w.wdown, H, I, 1), ring, q);
+                produce(make_slice(w.wo, H, QD, 1), ring, q, pf, p);
+                produce(make_slice(w.wgu, 2 * I, H, 2), ring, q, pf, p);
+                produce(make_slice(w.wdown, H, I, 1), ring, q, pf, p);
             }
-            produce(make_slice(p.lm_head, p.V, H, 1), ring, q);
+            produce(make_slice(p.lm_head, p.V, H, 1), ring, q, pf, p);
+            {   // warm L2 with the head of the NEXT step's stream (same addresses every step)
+                ChunkCursor<H, QD, I> nx;
+                nx.init(p);
+                const bf16* psrc; uint32_t pbytes;
+                for (int i = 0; i < PF_AHEAD; ++i) if (nx.next(p, psrc, pbytes)) l2_prefetch(psrc, pbytes);
+            }
         }
         return;
     }
@@ -374,8 +470,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                 if (warp < p.group) head_norm_rope(p.qkv_ll + (size_t)(g * p.group + warp) * HD, tl | PH_QKV, w.qnorm, p.eps, cs, sn, qs + warp * HD, lane);
                 else if (warp == p.group && has_new) head_norm_rope(p.qkv_ll + QD + (size_t)g * HD, tl | PH_QKV, w.knorm, p.eps, cs, sn, kn, lane);
                 else if (warp == p.group + 1 && has_new) {
+                    float vv[4];
+                    ll_poll4(p.qkv_ll + QD + p.KVD + (size_t)g * HD + lane, 32, tl | PH_QKV, vv);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) vn[lane + 32 * i] = ll_poll1(p.qkv_ll + QD + p.KVD + (size_t)g * HD + lane + 32 * i, tl | PH_QKV);
+                    for (int i = 0; i < 4; ++i) vn[lane + 32 * i] = vv[i];
                 }
                 if (n_old > 0) mbar_wait(kv_full, kvq & 1);      // prefetched K/V tiles have landed
                 cons_sync();
@@ -435,14 +533,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                 if (att_sp == 0) {
                     for (int idx = tid; idx < p.group * HD; idx += NCONS) {
                         const int hq = idx / HD, d = idx - hq * HD;
+                        // batches of 5 splits: all loads of a batch are issued before any tag is examined
+                        constexpr int SB = 5;
+                        const uint32_t tg = tl | PH_PART;
                         float M = -INFINITY, Lsum = 0.f, O = 0.f;
-                        for (int s2 = 0; s2 < nact; ++s2) {
-                            const uint2* rec = p.part_ll + ((size_t)(g * p.nsplit + s2) * p.group + hq) * PSTRIDE;
-                            const float ms = ll_poll1(rec + HD, tl | PH_PART), ls = ll_poll1(rec + HD + 1, tl | PH_PART);
-                            const float os = ll_poll1(rec + d, tl | PH_PART);
-                            const float Mn = fmaxf(M, ms);
-                            const float a = expf(M - Mn), b = expf(ms - Mn);     // exp(-inf) = 0 on the first split
-                            Lsum = Lsum * a + ls * b; O = O * a + os * b; M = Mn;
+                        for (int sb = 0; sb < nact; sb += SB) {
+                            uint2 mv[SB], lv[SB], ov[SB];
+                            bool ok;
+                            do {
+                                ok = true;
+#pragma unroll
+                                for (int u = 0; u < SB; ++u) {
+                                    if (sb + u < nact) {
+                                        const uint2* rec = p.part_ll + ((size_t)(g * p.nsplit + sb + u) * p.group + hq) * PSTRIDE;
+                                        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(mv[u].x), "=r"(mv[u].y) : "l"(rec + HD) : "memory");
+                                        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lv[u].x), "=r"(lv[u].y) : "l"(rec + HD + 1) : "memory");
+                                        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(ov[u].x), "=r"(ov[u].y) : "l"(rec + d) : "memory");
+                                    }
+                                }
+#pragma unroll
+                                for (int u = 0; u < SB; ++u)
+                                    if (sb + u < nact) ok = ok && (mv[u].y == tg) && (lv[u].y == tg) && (ov[u].y == tg);
+                            } while (!ok);
+#pragma unroll
+                            for (int u = 0; u < SB; ++u) {
+                                if (sb + u < nact) {
+                                    const float ms = __uint_as_float(mv[u].x), ls = __uint_as_float(lv[u].x), os = __uint_as_float(ov[u].x);
+                                    const float Mn = fmaxf(M, ms);
+                                    const float a = expf(M - Mn), b = expf(ms - Mn);     // exp(-inf) = 0 on the first split
+                                    Lsum = Lsum * a + ls * b; O = O * a + os * b; M = Mn;
+                                }
+                            }
                         }
                         ll_store(p.attn_ll + (size_t)(g * p.group + hq) * HD + d, O / Lsum, tl | PH_ATTN);
                     }
