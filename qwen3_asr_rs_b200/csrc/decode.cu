@@ -1,4 +1,5 @@
-// decode.cu -- one greedy decode iteration (inference.rs:160-200) as per-phase kernels, batch <= 8.
+// decode.cu -- one greedy decode iteration (inference.rs:160-200) as per-phase kernels, any batch
+// (processed in sub-batches of 8 sequences).
 //
 // This is the general-batch path and the on-device reference of the fused single-kernel step
 // (decode_mega.cu).  All phases are HBM-bandwidth kernels: each weight byte is read exactly once
@@ -12,6 +13,7 @@
 // then final RMSNorm + tied lm_head GEMV + argmax partials (text_decoder.rs:111-112) and the greedy
 // bookkeeping kernel (argmax, EOS check, append, embed next token; inference.rs:161-170) -- the
 // 151936 logits are only written in parity mode and no host sync happens per token.
+#include <algorithm>
 #include "internal.h"
 
 namespace asrb {
@@ -262,20 +264,34 @@ void launch_greedy(const Model& m, const DecodeBufs& b, int B, cudaStream_t st, 
     if (launches) *launches += 1;
 }
 
+static DecodeBufs offset_bufs(const DecodeBufs& b, int b0, const Model& m) {
+    const asrb_dims& c = m.d.c;
+    DecodeBufs o = b;
+    o.x = b.x + (size_t)b0 * c.hidden_size; o.qkv = b.qkv + (size_t)b0 * m.d.qkv_dim; o.attn = b.attn + (size_t)b0 * m.d.q_dim;
+    o.act = b.act + (size_t)b0 * c.intermediate_size; o.logits = b.logits ? b.logits + (size_t)b0 * c.vocab_size : nullptr;
+    o.part_val = b.part_val + (size_t)b0 * b.n_part; o.part_idx = b.part_idx + (size_t)b0 * b.n_part;
+    o.pos = b.pos + b0; o.done = b.done + b0; o.next_id = b.next_id + b0; o.ids_out = b.ids_out + (size_t)b0 * b.max_new; o.n_out = b.n_out + b0;
+    return o;
+}
+
 void launch_lmhead_argmax(const Model& m, const float* x_rows, const int* d_row_idx, int B, const DecodeBufs& b,
                           bool write_logits, cudaStream_t st, int64_t* launches) {
     const asrb_dims& c = m.d.c;
-    GemvParams p{};
-    p.W = m.lm_head; p.N = c.vocab_size; p.K = c.hidden_size;
-    p.x = x_rows; p.ldx = c.hidden_size; p.row_idx = d_row_idx;
-    p.norm_w = m.final_norm; p.eps = (float)c.rms_norm_eps;
-    p.logits = write_logits ? b.logits : nullptr; p.ldl = c.vocab_size;
-    p.part_val = b.part_val; p.part_idx = b.part_idx; p.B = B;
-    run_gemv<true, DE_ARGMAX>(p, b.n_part, st);
-    if (launches) *launches += 1;
+    for (int b0 = 0; b0 < B; b0 += 8) {              // GEMV kernels hold up to 8 activation vectors in shared memory
+        const int nb = std::min(8, B - b0);
+        const DecodeBufs ob = offset_bufs(b, b0, m);
+        GemvParams p{};
+        p.W = m.lm_head; p.N = c.vocab_size; p.K = c.hidden_size;
+        p.x = d_row_idx ? x_rows : x_rows + (size_t)b0 * c.hidden_size; p.ldx = c.hidden_size; p.row_idx = d_row_idx ? d_row_idx + b0 : nullptr;
+        p.norm_w = m.final_norm; p.eps = (float)c.rms_norm_eps;
+        p.logits = write_logits ? ob.logits : nullptr; p.ldl = c.vocab_size;
+        p.part_val = ob.part_val; p.part_idx = ob.part_idx; p.B = nb;
+        run_gemv<true, DE_ARGMAX>(p, b.n_part, st);
+        if (launches) *launches += 1;
+    }
 }
 
-void launch_decode_step_phases(const Model& m, const DecodeBufs& b, int B, float* kcache, float* vcache,
+void launch_decode_step_phases(const Model& m, const DecodeBufs& ball, int Ball, float* kcache_all, float* vcache_all,
                                size_t cache_layer_stride, size_t cache_seq_stride, int max_ctx, bool write_logits,
                                cudaStream_t st, int64_t* launches) {
     const asrb_dims& c = m.d.c;
@@ -289,7 +305,12 @@ void launch_decode_step_phases(const Model& m, const DecodeBufs& b, int B, float
         ASRB_CUDA_CHECK(cudaFuncSetAttribute(dec_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
         attn_smem_set = attn_smem;
     }
-    for (int l = 0; l < c.num_hidden_layers; ++l) {
+    for (int b0 = 0; b0 < Ball; b0 += 8) {           // sub-batches of 8 sequences (weights are re-streamed per sub-batch)
+      const int B = std::min(8, Ball - b0);
+      const DecodeBufs b = offset_bufs(ball, b0, m);
+      float* kcache = kcache_all + (size_t)b0 * cache_seq_stride;
+      float* vcache = vcache_all + (size_t)b0 * cache_seq_stride;
+      for (int l = 0; l < c.num_hidden_layers; ++l) {
         const DecLayerW& w = m.dec[l];
         GemvParams p{};
         p.B = B; p.eps = (float)c.rms_norm_eps;
@@ -319,8 +340,9 @@ void launch_decode_step_phases(const Model& m, const DecodeBufs& b, int B, float
         p.norm_w = nullptr; p.out = b.x; p.ldo = c.hidden_size;
         run_gemv<false, DE_RESID>(p, min(sms * 2, (p.N + 7) / 8), st);
         if (launches) *launches += 5;
+      }
     }
-    launch_lmhead_argmax(m, b.x, nullptr, B, b, write_logits, st, launches);
+    launch_lmhead_argmax(m, ball.x, nullptr, Ball, ball, write_logits, st, launches);
 }
 
 }  // namespace asrb

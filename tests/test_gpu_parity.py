@@ -213,3 +213,14 @@ def test_model_load_from_directory(tiny, tmp_path, shards):
     assert got.ids[0] == ref.ids
     with pytest.raises(AsrbError):
         AsrInference.load(str(tmp_path / "does_not_exist"), device=0)
+
+
+def test_token_ids_batch_larger_than_8(tiny, tiny_engine):
+    """batch > 8: the per-phase decode path walks sub-batches of 8 sequences; utterances stay independent
+    (the reference is batch-1, so batch semantics == B independent runs of it)."""
+    _, _, model = tiny
+    secs = [1.1, 2.3, 0.7, 4.9, 3.1, 1.9, 2.2, 0.9, 5.3, 1.4, 2.8]
+    clips = [synth.make_clip(200 + i, s) for i, s in enumerate(secs)]
+    got = tiny_engine.transcribe_ids(clips, max_new_tokens=10)
+    for g, c in zip(got.ids, clips):
+        assert g == O.transcribe_ids(model, c, max_new_tokens=10).ids
