@@ -32,6 +32,17 @@ sys.path.insert(0, ROOT)
 CLIP_SECONDS = 30.0
 
 
+def load_traffic():
+    """dram bytes per decode-step launch from the committed `ncu --set full` capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_decode_step_ncu_summary.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_read"] + d["dram_bytes_write"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -101,6 +112,9 @@ def cpu_reference_run(new_tokens: int, reps: int):
     import torch
     from oracle import oracle as O
     from qwen3_asr_rs_b200 import synth
+    if os.environ.get("OMP_NUM_THREADS") == "1" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # torchrun pins OMP_NUM_THREADS=1 per rank; the CPU arm runs on rank 0 alone and may use the host's cores
+        torch.set_num_threads(max(1, min(os.cpu_count() or 1, 64)))
     cfg = O.cfg_0p6b()
     model = O.OracleModel(cfg, synth.make_weights(cfg, 1))
     x = synth.make_clip(0, CLIP_SECONDS)
@@ -239,7 +253,8 @@ def main():
                 "decode": {"steps_per_clip": dec_steps // K, "us_per_step": 1e6 * step_s, "tokens": len(ids)},
                 "roofline": {"kernel": "decoder forward step (batch 1)", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
-                             "bytes_per_launch": step_bytes, "traffic": None},
+                             "bytes_per_launch": step_bytes, "traffic": load_traffic(),
+                             "traffic_source": "profiles/r01_decode_step_ncu_summary.json (ncu --set full, 1 launch)"},
                 "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             times, ref, cores = cpu_reference_run(args.new_tokens, 1)

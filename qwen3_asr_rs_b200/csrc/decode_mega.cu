@@ -60,6 +60,7 @@ struct Params {
     unsigned* bar;               // [0] finish ticket, [1] launch epoch (starts at 1; 0 marks never-written words)
     // tagged exchange buffers ({value, tag} words)
     uint2* qkv_ll; uint2* part_ll; uint2* attn_ll; uint2* x_ll; uint2* act_ll;
+    unsigned* cnt;               // [L + 1][8] arrival counters
     long long* dbg;              // optional timeline [2][DBG_SLOTS] of clock64 (CTA 0 and CTA G-1), else null
 };
 
@@ -92,18 +93,36 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
 
 // ---- tagged exchange ({fp32 value, tag} in one 64-bit word) ------------------------------------
+// Publication uses an atomic exchange: atomics are performed at L2 as soon as they are issued, whereas plain
+// or volatile stores were measured to linger for microseconds before becoming visible to other SMs, and a
+// release fence costs ~1 us (experiments/README.md).
 __device__ __forceinline__ void ll_store(uint2* p, float v, uint32_t tag) {
-    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+    const unsigned long long val = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+    unsigned long long old;
+    asm volatile("atom.relaxed.gpu.global.exch.b64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(val) : "memory");
+}
+// arrival counters: one per (layer, phase); every producing CTA adds 1 per step, so the value reached when all
+// `nprod` producers of step `epoch` have published is epoch * nprod (never reset).
+__device__ __forceinline__ void count_arrive(unsigned* c) {
+    cons_sync();                                   // all warps of this CTA have issued their publications
+    if (threadIdx.x == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(c) : "memory");
+}
+__device__ __forceinline__ void count_wait(const unsigned* c, unsigned target) {
+    if (threadIdx.x == 0) {
+        unsigned v;
+        do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory"); } while ((int)(v - target) < 0);
+    }
+    cons_sync();
 }
 __device__ __forceinline__ uint4 ll_load2(const uint2* p) {      // two consecutive words (16-byte aligned)
     uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ float ll_poll1(const uint2* p, uint32_t tag) {
     uint2 v;
     do {
-        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+        asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     } while (v.y != tag);
     return __uint_as_float(v.x);
 }
@@ -114,7 +133,7 @@ __device__ __forceinline__ void ll_poll4(const uint2* p, int stride, uint32_t ta
     do {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v[i].x), "=r"(v[i].y) : "l"(p + (size_t)i * stride) : "memory");
+            asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v[i].x), "=r"(v[i].y) : "l"(p + (size_t)i * stride) : "memory");
         ok = (v[0].y == tag) && (v[1].y == tag) && (v[2].y == tag) && (v[3].y == tag);
     } while (!ok);
 #pragma unroll
@@ -433,7 +452,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     const unsigned G = gridDim.x;
     float best_v = -INFINITY; int best_i = 0x7fffffff;
     // tag = launch epoch (unique per executed step, survives new utterances that revisit the same positions)
-    const uint32_t tag_base = (__ldcg(p.bar + 1) & 0xffffffu) << 8;
+    const unsigned epoch = __ldcg(p.bar + 1);
+    const uint32_t tag_base = (epoch & 0xffffffu) << 8;
 
     // residual rows owned by this CTA (same row partition for o_proj and down_proj)
     const Slice xsl = make_slice(nullptr, H, QD, 1);
@@ -446,10 +466,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
         {
             float ss = 0.f;
             if (l == 0) { for (int i = tid; i < H; i += NCONS) { const float v = __ldcg(p.x + i); xs[i] = v; ss = fmaf(v, v, ss); } }
-            else ss = ll_gather(p.x_ll, H, (tag_base | ((uint32_t)(l - 1) << 3)) | PH_XD, xs);
+            else { count_wait(p.cnt + (l - 1) * 8 + PH_XD, epoch * G); ss = ll_gather(p.x_ll, H, (tag_base | ((uint32_t)(l - 1) << 3)) | PH_XD, xs); }
             norm_in_smem(ss, w.ln_in, H, p.eps, xs, red);
         }
         consume<H, ME_STORE>(make_slice(w.wqkv, QD + 2 * p.KVD, H, 1), ring, q, xs, p.qkv_ll, tl | PH_QKV, xres, best_v, best_i);
+        count_arrive(p.cnt + l * 8 + PH_QKV);
         MEGA_MARK();
         // ---- phase 2: attention partials, work item = (kv head, 64-key split) ----
         {
@@ -466,7 +487,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                 float* Ks = reinterpret_cast<float*>(kv_smem);
                 float* Vs = reinterpret_cast<float*>(kv_smem + KV_TILE_BYTES);
                 const bool has_new = (pos >= att_j0) && (pos < att_j0 + KV_KEYS);
-                cons_sync();                          // xs (phase-1 activations) no longer needed by any warp
+                count_wait(p.cnt + l * 8 + PH_QKV, epoch * G);   // all q/k/v rows published (also: xs is free again)
                 if (warp < p.group) head_norm_rope(p.qkv_ll + (size_t)(g * p.group + warp) * HD, tl | PH_QKV, w.qnorm, p.eps, cs, sn, qs + warp * HD, lane);
                 else if (warp == p.group && has_new) head_norm_rope(p.qkv_ll + QD + (size_t)g * HD, tl | PH_QKV, w.knorm, p.eps, cs, sn, kn, lane);
                 else if (warp == p.group + 1 && has_new) {
@@ -546,9 +567,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                                 for (int u = 0; u < SB; ++u) {
                                     if (sb + u < nact) {
                                         const uint2* rec = p.part_ll + ((size_t)(g * p.nsplit + sb + u) * p.group + hq) * PSTRIDE;
-                                        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(mv[u].x), "=r"(mv[u].y) : "l"(rec + HD) : "memory");
-                                        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lv[u].x), "=r"(lv[u].y) : "l"(rec + HD + 1) : "memory");
-                                        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(ov[u].x), "=r"(ov[u].y) : "l"(rec + d) : "memory");
+                                        asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(mv[u].x), "=r"(mv[u].y) : "l"(rec + HD) : "memory");
+                                        asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(lv[u].x), "=r"(lv[u].y) : "l"(rec + HD + 1) : "memory");
+                                        asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(ov[u].x), "=r"(ov[u].y) : "l"(rec + d) : "memory");
                                     }
                                 }
 #pragma unroll
@@ -567,34 +588,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                         }
                         ll_store(p.attn_ll + (size_t)(g * p.group + hq) * HD + d, O / Lsum, tl | PH_ATTN);
                     }
+                    count_arrive(p.cnt + l * 8 + PH_ATTN);
                 }
                 cons_sync();                          // attention scratch (aliases xs) is free again
             }
         }
         MEGA_MARK();
         // ---- phase 3: o_proj GEMV + residual ----
+        count_wait(p.cnt + l * 8 + PH_ATTN, epoch * (unsigned)p.nkv);
         ll_gather(p.attn_ll, QD, tl | PH_ATTN, xs);
         cons_sync();
         consume<QD, ME_RESID>(make_slice(w.wo, H, QD, 1), ring, q, xs, p.x_ll, tl | PH_XO, xres, best_v, best_i);
+        count_arrive(p.cnt + l * 8 + PH_XO);
         MEGA_MARK();
         // ---- phase 4: RMSNorm + gate/up GEMV + SiLU*mul ----
         cons_sync();
         {
+            count_wait(p.cnt + l * 8 + PH_XO, epoch * G);
             const float ss = ll_gather(p.x_ll, H, tl | PH_XO, xs);
             norm_in_smem(ss, w.ln_post, H, p.eps, xs, red);
         }
         consume<H, ME_SWIGLU>(make_slice(w.wgu, 2 * I, H, 2), ring, q, xs, p.act_ll, tl | PH_ACT, xres, best_v, best_i);
+        count_arrive(p.cnt + l * 8 + PH_ACT);
         MEGA_MARK();
         // ---- phase 5: down GEMV + residual ----
-        cons_sync();
+        count_wait(p.cnt + l * 8 + PH_ACT, epoch * G);
         ll_gather(p.act_ll, I, tl | PH_ACT, xs);
         cons_sync();
         consume<I, ME_RESID>(make_slice(w.wdown, H, I, 1), ring, q, xs, p.x_ll, tl | PH_XD, xres, best_v, best_i);
+        count_arrive(p.cnt + l * 8 + PH_XD);
         MEGA_MARK();
         cons_sync();
     }
     // ---- final RMSNorm + tied lm_head GEMV + argmax ----
     {
+        count_wait(p.cnt + (p.L - 1) * 8 + PH_XD, epoch * G);
         const float ss = ll_gather(p.x_ll, H, (tag_base | ((uint32_t)(p.L - 1) << 3)) | PH_XD, xs);
         norm_in_smem(ss, p.final_norm, H, p.eps, xs, red);
     }
@@ -685,7 +713,7 @@ size_t decode_mega_part_floats(const Model& m) {
     const int group = c.num_attention_heads / c.num_key_value_heads;
     const size_t words = (size_t)m.d.qkv_dim + (size_t)m.ctx->sm_count * group * mega::PSTRIDE + m.d.q_dim + c.hidden_size +
                          c.intermediate_size + 64;
-    return 2 * words;
+    return 2 * words + (size_t)(c.num_hidden_layers + 1) * 8 + 64;     // tagged words + arrival counters
 }
 
 void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* kcache, float* vcache,
@@ -713,7 +741,8 @@ void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* 
     p.part_ll = w; w += (size_t)G * group * mega::PSTRIDE;
     p.attn_ll = w; w += m.d.q_dim;
     p.x_ll = w; w += c.hidden_size;
-    p.act_ll = w;
+    p.act_ll = w; w += c.intermediate_size;
+    p.cnt = reinterpret_cast<unsigned*>(w);
     p.dbg = mb.dbg;
     g_last_dbg = mb.dbg;
     const size_t smem = mega_smem_bytes();
