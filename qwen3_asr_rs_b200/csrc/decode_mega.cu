@@ -35,7 +35,8 @@ static constexpr int NSLOT = 5;                         // weight ring: 120 KB i
 static constexpr int KV_KEYS = 64;                      // keys per attention split (K and V tiles staged in smem)
 static constexpr int KV_TILE_BYTES = KV_KEYS * 128 * 4; // 32 KB each for K and V (fp32 cache)
 static constexpr int XS_FLOATS = 3072 + 64;             // activation vector / attention scratch
-static constexpr int XRES_MAX = 64;                     // residual rows owned by one CTA (H / gridDim.x, rounded up)
+static constexpr int XRES_MAX = 64;
+static constexpr int MAX_LAYERS = 32;                   // layer table staged in shared memory                     // residual rows owned by one CTA (H / gridDim.x, rounded up)
 static constexpr int HD = 128;
 static constexpr int PSTRIDE = HD + 2;                  // partial record: o[128], m, l
 static constexpr int DBG_SLOTS = 512;
@@ -196,16 +197,17 @@ static constexpr int PF_AHEAD = 0;    // measured: distances 16 / 4 / 0 give the
 template <int H, int QD, int I>
 struct ChunkCursor {
     int l, ph, r; Slice s; bool done;
+    const DecLayerW* ltab;
     __device__ void load(const Params& p) {
         if (l >= p.L) { if (l == p.L && ph == 0) s = make_slice(p.lm_head, p.V, H, 1); else { done = true; return; } }
         else {
-            const DecLayerW w = p.layers[l];
+            const DecLayerW w = ltab[l];
             s = ph == 0 ? make_slice(w.wqkv, QD + 2 * p.KVD, H, 1) : ph == 1 ? make_slice(w.wo, H, QD, 1)
               : ph == 2 ? make_slice(w.wgu, 2 * I, H, 2) : make_slice(w.wdown, H, I, 1);
         }
         r = s.r0;
     }
-    __device__ void init(const Params& p) { l = 0; ph = 0; done = false; load(p); }
+    __device__ void init(const Params& p, const DecLayerW* table) { ltab = table; l = 0; ph = 0; done = false; load(p); }
     __device__ bool next(const Params& p, const bf16*& src, uint32_t& bytes) {
         while (!done && r >= s.r1) {
             if (l >= p.L) { done = true; break; }
@@ -369,15 +371,20 @@ __device__ __forceinline__ void head_norm_rope(const uint2* __restrict__ src, ui
 template <int H, int QD, int I>
 __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int PARAM_FLOATS = 2 * H + 2 * HD;      // per-layer small vectors: ln_in[H], ln_post[H], q_norm[128], k_norm[128]
     Ring ring;
     ring.slots = smem;
     uint8_t* kv_smem = smem + (size_t)NSLOT * SLOT_BYTES;              // [K tile | V tile]
     float* xs = reinterpret_cast<float*>(kv_smem + 2 * KV_TILE_BYTES);
     float* xres = xs + XS_FLOATS;                                      // [XRES_MAX] residual rows owned by this CTA
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xres + XRES_MAX);
+    float* pbuf = xres + XRES_MAX;                                     // [2][PARAM_FLOATS] per-layer small vectors (double buffer)
+    float* ropes = pbuf + 2 * PARAM_FLOATS;                            // [128] cos | sin of this step's position
+    DecLayerW* ltab = reinterpret_cast<DecLayerW*>(ropes + 128);       // [MAX_LAYERS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ltab + MAX_LAYERS);
     ring.full = bars; ring.empty = bars + NSLOT;
     uint64_t* kv_full = bars + 2 * NSLOT; uint64_t* kv_empty = kv_full + 1;
-    float* red = reinterpret_cast<float*>(bars + 2 * NSLOT + 2);      // [64]
+    uint64_t* p_full = kv_empty + 1; uint64_t* p_empty = p_full + 2;   // [2] each
+    float* red = reinterpret_cast<float*>(bars + 2 * NSLOT + 6);      // [64]
     int* ired = reinterpret_cast<int*>(red + 64);                      // [64]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_producer = warp == NCONS_WARPS;
@@ -387,13 +394,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     if (tid == 0) {
         for (int i = 0; i < NSLOT; ++i) { mbar_init(&ring.full[i], 1); mbar_init(&ring.empty[i], NCONS_WARPS); }
         mbar_init(kv_full, 1); mbar_init(kv_empty, NCONS_WARPS);
+        for (int i = 0; i < 2; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], NCONS_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // Small read-only tables go to shared memory: with 1.2 GB streaming through L2 every step they are never
+    // L2-resident, and a dependent DRAM round trip (~1-2 us) per use is what the phases cannot afford.
+    const int pos = __ldcg(p.pos);
+    {
+        const uint2* src = reinterpret_cast<const uint2*>(p.layers);
+        uint2* dst = reinterpret_cast<uint2*>(ltab);
+        for (int i = tid; i < p.L * (int)(sizeof(DecLayerW) / 8); i += NTHREADS) dst[i] = src[i];
+        if (tid < 64) ropes[tid] = p.rope_cos[(size_t)pos * 64 + tid];
+        else if (tid < 128) ropes[tid] = p.rope_sin[(size_t)pos * 64 + tid - 64];
     }
     __syncthreads();
 
     // attention work item of this CTA: (kv head att_g, keys [att_j0, att_j0 + KV_KEYS)); keys < pos are
     // already in the cache (n_old of them fall in this split), key `pos` is produced in this step.
-    const int pos = __ldcg(p.pos);
     const bool att_cta = (int)blockIdx.x < p.nkv * p.nsplit;
     const int att_g = blockIdx.x / p.nsplit, att_sp = blockIdx.x % p.nsplit, att_j0 = att_sp * KV_KEYS;
     const int n_old = att_cta ? max(0, min(pos - att_j0, KV_KEYS)) : 0;
@@ -402,7 +419,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     if (is_producer) {
         if (lane == 0) {
             ChunkCursor<H, QD, I> pf;
-            pf.init(p);
+            pf.init(p, ltab);
             {   // start the HBM stream immediately: the first PF_AHEAD chunks go to L2 now
                 const bf16* psrc; uint32_t pbytes;
                 for (int i = 0; i < PF_AHEAD; ++i) if (pf.next(p, psrc, pbytes)) l2_prefetch(psrc, pbytes);
@@ -412,8 +429,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                 l2_prefetch(p.kcache + kv_row, (uint32_t)n_old * HD * 4);
                 l2_prefetch(p.vcache + kv_row, (uint32_t)n_old * HD * 4);
             }
-            for (int l = 0; l < p.L; ++l) {
-                const DecLayerW w = p.layers[l];
+            for (int l = 0; l <= p.L; ++l) {
+                {   // small per-layer vectors -> pbuf[l & 1] (layer L = final norm only)
+                    float* pb = pbuf + (l & 1) * PARAM_FLOATS;
+                    mbar_wait(&p_empty[l & 1], ((l >> 1) & 1) ^ 1);
+                    if (l < p.L) {
+                        const DecLayerW w = ltab[l];
+                        mbar_expect_tx(&p_full[l & 1], (uint32_t)(2 * H + 2 * HD) * 4);
+                        bulk_g2s(pb, w.ln_in, H * 4, &p_full[l & 1]);
+                        bulk_g2s(pb + H, w.ln_post, H * 4, &p_full[l & 1]);
+                        bulk_g2s(pb + 2 * H, w.qnorm, HD * 4, &p_full[l & 1]);
+                        bulk_g2s(pb + 2 * H + HD, w.knorm, HD * 4, &p_full[l & 1]);
+                    } else {
+                        mbar_expect_tx(&p_full[l & 1], (uint32_t)H * 4);
+                        bulk_g2s(pb, p.final_norm, H * 4, &p_full[l & 1]);
+                        break;
+                    }
+                }
+                const DecLayerW w = ltab[l];
                 produce(make_slice(w.wqkv, QD + 2 * p.KVD, H, 1), ring, q, pf, p);
                 if (n_old > 0) {   // K/V rows of earlier positions do not depend on this step: prefetch them too
                     const uint32_t bytes = (uint32_t)n_old * HD * 4;
@@ -435,7 +468,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
             produce(make_slice(p.lm_head, p.V, H, 1), ring, q, pf, p);
             {   // warm L2 with the head of the NEXT step's stream (same addresses every step)
                 ChunkCursor<H, QD, I> nx;
-                nx.init(p);
+                nx.init(p, ltab);
                 const bf16* psrc; uint32_t pbytes;
                 for (int i = 0; i < PF_AHEAD; ++i) if (nx.next(p, psrc, pbytes)) l2_prefetch(psrc, pbytes);
             }
@@ -448,8 +481,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     if (p.dbg && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) dbg_row = p.dbg + (blockIdx.x == 0 ? 0 : DBG_SLOTS);
     MEGA_MARK();
     const int half = HD / 2;
-    const float* cs = p.rope_cos + (size_t)pos * half;
-    const float* sn = p.rope_sin + (size_t)pos * half;
+    const float* cs = ropes;
+    const float* sn = ropes + half;
     const unsigned G = gridDim.x;
     float best_v = -INFINITY; int best_i = 0x7fffffff;
     // tag = launch epoch (unique per executed step, survives new utterances that revisit the same positions)
@@ -461,14 +494,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     for (int i = tid; i < xsl.r1 - xsl.r0; i += NCONS) xres[i] = __ldcg(p.x + xsl.r0 + i);
 
     for (int l = 0; l < p.L; ++l) {
-        const DecLayerW w = p.layers[l];
+        const DecLayerW w = ltab[l];
         const uint32_t tl = tag_base | ((uint32_t)l << 3);
+        const float* pb = pbuf + (l & 1) * PARAM_FLOATS;               // ln_in | ln_post | q_norm | k_norm of this layer
+        mbar_wait(&p_full[l & 1], (l >> 1) & 1);
         // ---- phase 1: RMSNorm + [q|k|v] GEMV ----
         {
             float ss = 0.f;
             if (l == 0) { for (int i = tid; i < H; i += NCONS) { const float v = __ldcg(p.x + i); xs[i] = v; ss = fmaf(v, v, ss); } }
             else { count_wait(p.cnt + (l - 1) * 8 + PH_XD, epoch * G); ss = ll_gather(p.x_ll, H, (tag_base | ((uint32_t)(l - 1) << 3)) | PH_XD, xs); }
-            norm_in_smem(ss, w.ln_in, H, p.eps, xs, red);
+            norm_in_smem(ss, pb, H, p.eps, xs, red);
         }
         consume<H, ME_STORE>(make_slice(w.wqkv, QD + 2 * p.KVD, H, 1), ring, q, xs, p.qkv_ll, tl | PH_QKV, xres, best_v, best_i);
         count_arrive(p.cnt + l * 8 + PH_QKV);
@@ -489,8 +524,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                 float* Vs = reinterpret_cast<float*>(kv_smem + KV_TILE_BYTES);
                 const bool has_new = (pos >= att_j0) && (pos < att_j0 + KV_KEYS);
                 count_wait(p.cnt + l * 8 + PH_QKV, epoch * G);   // all q/k/v rows published (also: xs is free again)
-                if (warp < p.group) head_norm_rope(p.qkv_ll + (size_t)(g * p.group + warp) * HD, tl | PH_QKV, w.qnorm, p.eps, cs, sn, qs + warp * HD, lane);
-                else if (warp == p.group && has_new) head_norm_rope(p.qkv_ll + QD + (size_t)g * HD, tl | PH_QKV, w.knorm, p.eps, cs, sn, kn, lane);
+                if (warp < p.group) head_norm_rope(p.qkv_ll + (size_t)(g * p.group + warp) * HD, tl | PH_QKV, pb + 2 * H, p.eps, cs, sn, qs + warp * HD, lane);
+                else if (warp == p.group && has_new) head_norm_rope(p.qkv_ll + QD + (size_t)g * HD, tl | PH_QKV, pb + 2 * H + HD, p.eps, cs, sn, kn, lane);
                 else if (warp == p.group + 1 && has_new) {
                     float vv[4];
                     ll_poll4(p.qkv_ll + QD + p.KVD + (size_t)g * HD + lane, 32, tl | PH_QKV, vv);
@@ -607,7 +642,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
         {
             count_wait(p.cnt + l * 8 + PH_XO, epoch * G);
             const float ss = ll_gather(p.x_ll, H, tl | PH_XO, xs);
-            norm_in_smem(ss, w.ln_post, H, p.eps, xs, red);
+            norm_in_smem(ss, pb + H, H, p.eps, xs, red);
         }
         consume<H, ME_SWIGLU>(make_slice(w.wgu, 2 * I, H, 2), ring, q, xs, p.act_ll, tl | PH_ACT, xres, best_v, best_i);
         count_arrive(p.cnt + l * 8 + PH_ACT);
@@ -620,12 +655,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
         count_arrive(p.cnt + l * 8 + PH_XD);
         MEGA_MARK();
         cons_sync();
+        if (lane == 0) mbar_arrive(&p_empty[l & 1]);                   // this layer's parameter buffer may be refilled
     }
     // ---- final RMSNorm + tied lm_head GEMV + argmax ----
     {
         count_wait(p.cnt + (p.L - 1) * 8 + PH_XD, epoch * G);
         const float ss = ll_gather(p.x_ll, H, (tag_base | ((uint32_t)(p.L - 1) << 3)) | PH_XD, xs);
-        norm_in_smem(ss, p.final_norm, H, p.eps, xs, red);
+        mbar_wait(&p_full[p.L & 1], (p.L >> 1) & 1);
+        norm_in_smem(ss, pbuf + (p.L & 1) * PARAM_FLOATS, H, p.eps, xs, red);
     }
     consume<H, ME_ARGMAX>(make_slice(p.lm_head, p.V, H, 1), ring, q, xs, nullptr, 0u, xres, best_v, best_i);
     MEGA_MARK();
@@ -686,9 +723,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
 // host side ---------------------------------------------------------------------------------------
 static long long* g_last_dbg = nullptr;   // debug only (ASRB_MEGA_DEBUG): timeline buffer of the last launch
 
-static size_t mega_smem_bytes() {
-    return (size_t)mega::NSLOT * mega::SLOT_BYTES + 2 * mega::KV_TILE_BYTES + (mega::XS_FLOATS + mega::XRES_MAX) * 4 +
-           (2 * mega::NSLOT + 2) * 8 + 64 * 4 + 64 * 4 + 64;
+static size_t mega_smem_bytes(int H = 1024) {
+    return (size_t)mega::NSLOT * mega::SLOT_BYTES + 2 * mega::KV_TILE_BYTES +
+           (mega::XS_FLOATS + mega::XRES_MAX + 2 * (2 * H + 2 * mega::HD) + 128) * 4 + mega::MAX_LAYERS * sizeof(DecLayerW) +
+           (2 * mega::NSLOT + 6) * 8 + 64 * 4 + 64 * 4 + 64;
 }
 
 template <int H, int QD, int I> static bool dims_match(const asrb_dims& c) {
@@ -746,7 +784,7 @@ void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* 
     p.cnt = reinterpret_cast<unsigned*>(w);
     p.dbg = mb.dbg;
     g_last_dbg = mb.dbg;
-    const size_t smem = mega_smem_bytes();
+    const size_t smem = mega_smem_bytes(c.hidden_size);
     void* args[] = {(void*)&p};
     const void* fn = nullptr;
     if (dims_match<1024, 2048, 3072>(c)) fn = (const void*)mega::decode_step_kernel<1024, 2048, 3072>;
