@@ -144,19 +144,25 @@ __device__ __forceinline__ void ll_poll4(const uint2* p, int stride, uint32_t ta
 __device__ __forceinline__ float ll_gather(const uint2* buf, int n, uint32_t tag, float* xs) {
     float ss = 0.f;
     const int pairs = n >> 1;
-    for (int i0 = threadIdx.x; i0 < pairs; i0 += 4 * NCONS) {      // up to 4 independent 16-byte loads in flight
-        uint4 v[4];
+    constexpr int U = 8;                                           // independent 16-byte loads in flight per thread
+    for (int i0 = threadIdx.x; i0 < pairs; i0 += U * NCONS) {
+        uint4 v[U];
         bool ok;
         do {
             ok = true;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const int i = i0 + u * NCONS;
-                if (i < pairs) { v[u] = ll_load2(buf + 2 * i); ok = ok && (v[u].y == tag) && (v[u].w == tag); }
+                if (i < pairs) { v[u] = ll_load2(buf + 2 * i); }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * NCONS;
+                if (i < pairs) ok = ok && (v[u].y == tag) && (v[u].w == tag);
             }
         } while (!ok);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int i = i0 + u * NCONS;
             if (i < pairs) {
                 const float a = __uint_as_float(v[u].x), b = __uint_as_float(v[u].z);
@@ -590,36 +596,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                 if (att_sp == 0) {
                     for (int idx = tid; idx < p.group * HD; idx += NCONS) {
                         const int hq = idx / HD, d = idx - hq * HD;
-                        // batches of 5 splits: all loads of a batch are issued before any tag is examined
-                        constexpr int SB = 5;
+                        // lane s of every warp fetches (max, sum) of split s; every thread fetches o[s][d] of all active
+                        // splits; all loads are issued before any tag is examined (one round trip when ready)
+                        constexpr int SB = 10;                       // nsplit <= 10 enforced by decode_mega_supported
                         const uint32_t tg = tl | PH_PART;
-                        float M = -INFINITY, Lsum = 0.f, O = 0.f;
-                        for (int sb = 0; sb < nact; sb += SB) {
-                            uint2 mv[SB], lv[SB], ov[SB];
-                            bool ok;
-                            do {
-                                ok = true;
-#pragma unroll
-                                for (int u = 0; u < SB; ++u) {
-                                    if (sb + u < nact) {
-                                        const uint2* rec = p.part_ll + ((size_t)(g * p.nsplit + sb + u) * p.group + hq) * PSTRIDE;
-                                        asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(mv[u].x), "=r"(mv[u].y) : "l"(rec + HD) : "memory");
-                                        asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(lv[u].x), "=r"(lv[u].y) : "l"(rec + HD + 1) : "memory");
-                                        asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(ov[u].x), "=r"(ov[u].y) : "l"(rec + d) : "memory");
-                                    }
-                                }
-#pragma unroll
-                                for (int u = 0; u < SB; ++u)
-                                    if (sb + u < nact) ok = ok && (mv[u].y == tg) && (lv[u].y == tg) && (ov[u].y == tg);
-                            } while (!ok);
+                        uint2 ov[SB], mv, lv;
+                        bool ok;
+                        do {
+                            ok = true;
+                            mv.y = tg; lv.y = tg; mv.x = 0u; lv.x = 0u;
+                            if (lane < nact) {
+                                const uint2* rec = p.part_ll + ((size_t)(g * p.nsplit + lane) * p.group + hq) * PSTRIDE;
+                                asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(mv.x), "=r"(mv.y) : "l"(rec + HD) : "memory");
+                                asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(lv.x), "=r"(lv.y) : "l"(rec + HD + 1) : "memory");
+                            }
 #pragma unroll
                             for (int u = 0; u < SB; ++u) {
-                                if (sb + u < nact) {
-                                    const float ms = __uint_as_float(mv[u].x), ls = __uint_as_float(lv[u].x), os = __uint_as_float(ov[u].x);
-                                    const float Mn = fmaxf(M, ms);
-                                    const float a = expf(M - Mn), b = expf(ms - Mn);     // exp(-inf) = 0 on the first split
-                                    Lsum = Lsum * a + ls * b; O = O * a + os * b; M = Mn;
+                                if (u < nact) {
+                                    const uint2* rec = p.part_ll + ((size_t)(g * p.nsplit + u) * p.group + hq) * PSTRIDE;
+                                    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(ov[u].x), "=r"(ov[u].y) : "l"(rec + d) : "memory");
                                 }
+                            }
+                            ok = (mv.y == tg) && (lv.y == tg);
+#pragma unroll
+                            for (int u = 0; u < SB; ++u) if (u < nact) ok = ok && (ov[u].y == tg);
+                            ok = __all_sync(0xffffffffu, ok);
+                        } while (!ok);
+                        float M = -INFINITY, Lsum = 0.f, O = 0.f;
+#pragma unroll
+                        for (int u = 0; u < SB; ++u) {
+                            if (u < nact) {
+                                const float ms = __uint_as_float(__shfl_sync(0xffffffffu, mv.x, u));
+                                const float ls = __uint_as_float(__shfl_sync(0xffffffffu, lv.x, u));
+                                const float os = __uint_as_float(ov[u].x);
+                                const float Mn = fmaxf(M, ms);
+                                const float a = expf(M - Mn), b = expf(ms - Mn);     // exp(-inf) = 0 on the first split
+                                Lsum = Lsum * a + ls * b; O = O * a + os * b; M = Mn;
                             }
                         }
                         ll_store(p.attn_ll + (size_t)(g * p.group + hq) * HD + d, O / Lsum, tl | PH_ATTN);
@@ -742,6 +754,7 @@ bool decode_mega_supported(const Model& m, int B, int max_ctx) {
     if (m.ctx->smem_optin < mega_smem_bytes()) return false;
     if ((c.hidden_size + m.ctx->sm_count - 1) / m.ctx->sm_count + 1 > mega::XRES_MAX) return false;
     if (c.num_hidden_layers > 32) return false;                  // 5-bit layer field
+    if ((max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS > 10) return false;                           // merge loop bound (SB)
     if (((max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS) * c.num_key_value_heads > m.ctx->sm_count) return false;   // one CTA per (kv head, 64-key split)
     return dims_match<1024, 2048, 3072>(c) || dims_match<256, 512, 512>(c);
 }
