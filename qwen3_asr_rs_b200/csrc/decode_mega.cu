@@ -512,7 +512,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
             norm_in_smem(ss, pb, H, p.eps, xs, red);
         }
         consume<H, ME_STORE>(make_slice(w.wqkv, QD + 2 * p.KVD, H, 1), ring, q, xs, p.qkv_ll, tl | PH_QKV, xres, best_v, best_i);
-        count_arrive(p.cnt + l * 8 + PH_QKV);
         MEGA_MARK();
         // ---- phase 2: attention partials, work item = (kv head, 64-key split) ----
         {
@@ -529,7 +528,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                 float* Ks = reinterpret_cast<float*>(kv_smem);
                 float* Vs = reinterpret_cast<float*>(kv_smem + KV_TILE_BYTES);
                 const bool has_new = (pos >= att_j0) && (pos < att_j0 + KV_KEYS);
-                count_wait(p.cnt + l * 8 + PH_QKV, epoch * G);   // all q/k/v rows published (also: xs is free again)
+                cons_sync();                          // xs (phase-1 activations) no longer needed by any warp; q/k/v words are
+                                                      // polled directly below (few readers per word: no counter needed)
                 if (warp < p.group) head_norm_rope(p.qkv_ll + (size_t)(g * p.group + warp) * HD, tl | PH_QKV, pb + 2 * H, p.eps, cs, sn, qs + warp * HD, lane);
                 else if (warp == p.group && has_new) head_norm_rope(p.qkv_ll + QD + (size_t)g * HD, tl | PH_QKV, pb + 2 * H + HD, p.eps, cs, sn, kn, lane);
                 else if (warp == p.group + 1 && has_new) {
