@@ -162,7 +162,29 @@ __device__ __forceinline__ void epi_store8(const GemmEpi& e, int N, int m, int n
         float* o = e.out_f32 + (size_t)tok * e.ldo + n;
         *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    } else {   // EPI_SWIGLU (4 outputs from 8 columns) and EPI_CONV_FEAT (strided): pairwise path
+    } else if (MODE == EPI_SWIGLU) {   // 8 interleaved columns (gate_j, up_j) x 4 -> 4 outputs, one 8-byte store per plane
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = silu(acc[2 * i]) * acc[2 * i + 1];
+        const size_t idx = (size_t)m * e.lds + (n >> 1);
+        if (e.out_f32) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) e.out_f32[(size_t)m * e.ldo + (n >> 1) + i] = o[i];
+        }
+        if (e.out_s3) {
+            uint32_t hi[2], mid[2], lo[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                Split3 a = split3(o[2 * i]), b = split3(o[2 * i + 1]);
+                hi[i] = (uint32_t)__bfloat16_as_ushort(a.hi) | ((uint32_t)__bfloat16_as_ushort(b.hi) << 16);
+                mid[i] = (uint32_t)__bfloat16_as_ushort(a.mid) | ((uint32_t)__bfloat16_as_ushort(b.mid) << 16);
+                lo[i] = (uint32_t)__bfloat16_as_ushort(a.lo) | ((uint32_t)__bfloat16_as_ushort(b.lo) << 16);
+            }
+            *reinterpret_cast<uint2*>(e.out_s3 + idx) = make_uint2(hi[0], hi[1]);
+            *reinterpret_cast<uint2*>(e.out_s3 + e.s3_plane_stride + idx) = make_uint2(mid[0], mid[1]);
+            *reinterpret_cast<uint2*>(e.out_s3 + 2 * e.s3_plane_stride + idx) = make_uint2(lo[0], lo[1]);
+        }
+    } else {   // EPI_CONV_FEAT (strided): pairwise path
 #pragma unroll
         for (int i = 0; i < 8; i += 2) epi_store2(e, N, m, n + i, acc[i], acc[i + 1], true);
     }
