@@ -745,7 +745,9 @@ template <int H, int QD, int I> static bool dims_match(const asrb_dims& c) {
     return c.hidden_size == H && c.num_attention_heads * c.head_dim == QD && c.intermediate_size == I;
 }
 
-bool decode_mega_supported(const Model& m, int B, int max_ctx) {
+// `ctx` = number of keys the step may attend to (position + 1 upper bound), NOT the cache capacity
+bool decode_mega_supported(const Model& m, int B, int ctx) {
+    const int max_ctx = ctx;
     const asrb_dims& c = m.d.c;
     if (B != 1 || c.head_dim != 128) return false;
     const int group = c.num_attention_heads / c.num_key_value_heads;
@@ -769,15 +771,16 @@ size_t decode_mega_part_floats(const Model& m) {
 }
 
 void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* kcache, float* vcache,
-                             size_t cache_layer_stride, size_t cache_seq_stride, int max_ctx, const MegaBufs& mb,
+                             size_t cache_layer_stride, size_t cache_seq_stride, int max_ctx, int ctx_now, const MegaBufs& mb,
                              cudaStream_t st, int64_t* launches) {
     (void)cache_seq_stride;
-    ASRB_REQUIRE(decode_mega_supported(m, B, max_ctx), ASRB_ERR_STATE, "fused decode step not supported for this model/batch");
+    ASRB_REQUIRE(decode_mega_supported(m, B, ctx_now), ASRB_ERR_STATE, "fused decode step not supported for this model/batch/context");
     ASRB_REQUIRE(m.d_dec_layers && mb.bar && mb.part, ASRB_ERR_STATE, "fused decode step buffers missing");
     const asrb_dims& c = m.d.c;
     const int G = m.ctx->sm_count;
     const int group = c.num_attention_heads / c.num_key_value_heads;
-    const int nsplit = (max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS;
+    // split count is fixed per session (buffer layout); splits beyond the current context are simply empty
+    const int nsplit = std::min(10, std::min(G / c.num_key_value_heads, (max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS));
     mega::Params p{};
     p.layers = m.d_dec_layers; p.lm_head = m.lm_head; p.embed = m.embed; p.final_norm = m.final_norm;
     p.rope_cos = m.rope_cos; p.rope_sin = m.rope_sin; p.eps = (float)c.rms_norm_eps;

@@ -426,21 +426,23 @@ void session_prefill(Session* s, const int64_t* const* lang_ids, const int32_t* 
 // -------------------------------------------------------------------------------------------------
 bool decode_mega_supported(const Model& m, int B, int max_ctx);
 void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* kcache, float* vcache,
-                             size_t cache_layer_stride, size_t cache_seq_stride, int max_ctx, const MegaBufs& mb,
+                             size_t cache_layer_stride, size_t cache_seq_stride, int max_ctx, int ctx_now, const MegaBufs& mb,
                              cudaStream_t st, int64_t* launches);
 size_t decode_mega_part_floats(const Model& m);
 int decode_mega_dbg_slots();
 
 // one iteration of the loop body: decoder forward on the pending token, then the greedy bookkeeping
 // that selects / appends / embeds the next one.  (The fused kernel does both.)
+// upper bound of (position + 1) for the next forward: prompt length + tokens appended so far
+static int ctx_bound(const Session* s) { return std::min(s->max_ctx, s->maxlenS + s->greedy_done); }
 static bool use_mega(Session* s, bool write_logits) {
-    return s->decode_mode == 1 && !write_logits && decode_mega_supported(*s->m, s->B, s->max_ctx);
+    return s->decode_mode == 1 && !write_logits && decode_mega_supported(*s->m, s->B, ctx_bound(s));
 }
 static void forward_step(Session* s, bool write_logits) {
     Model& m = *s->m;
     if (use_mega(s, write_logits)) {
         launch_decode_step_mega(m, s->db, s->B, s->kcache, s->vcache, s->cache_layer_stride, s->cache_seq_stride, s->max_ctx,
-                                s->mega, s->st, &s->launches);
+                                ctx_bound(s), s->mega, s->st, &s->launches);
     } else {
         launch_decode_step_phases(m, s->db, s->B, s->kcache, s->vcache, s->cache_layer_stride, s->cache_seq_stride, s->max_ctx,
                                   write_logits, s->st, &s->launches);
@@ -470,8 +472,7 @@ void session_generate(Session* s, int max_new_tokens, int32_t* ids_out, int32_t*
     // reference also runs `forward` after the last appended token and discards its logits
     // (inference.rs:160-200); that wasted forward is not issued here.
     const int steps = std::max(0, max_new_tokens - s->greedy_done);
-    const bool mega = use_mega(s, false);
-    if (!mega) {   // per-phase path: ~142 launches per step -> replay them as one CUDA graph
+    auto ensure_graph = [&]() {   // per-phase path: ~142 launches per step -> replay them as one CUDA graph
         const int mode_key = s->decode_mode * 16 + B;
         if (s->step_graph == nullptr || s->graph_mode != mode_key) {
             if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = nullptr; }
@@ -486,12 +487,13 @@ void session_generate(Session* s, int max_new_tokens, int32_t* ids_out, int32_t*
             s->graph_mode = mode_key; s->graph_B = (int)(s->launches - before);   // kernels per replay
             s->launches = before;
         }
-    }
+    };
     const int check_every = 16;
     bool all_done = false;
     for (int it = 0; it < steps && !all_done; ++it) {
-        if (mega) forward_step(s, false);
-        else { ASRB_CUDA_CHECK(cudaGraphLaunch(s->step_graph, st)); s->launches += s->graph_B; }
+        // the fused step covers contexts up to 640 keys; beyond that (long generations) the per-phase path takes over
+        if (use_mega(s, false)) forward_step(s, false);
+        else { ensure_graph(); ASRB_CUDA_CHECK(cudaGraphLaunch(s->step_graph, st)); s->launches += s->graph_B; }
         s->decode_steps += 1; s->greedy_done += 1;
         if ((it + 1) % check_every == 0 && it + 1 < steps) {
             ASRB_CUDA_CHECK(cudaMemcpyAsync(s->h_done, s->db.done, B * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -43,6 +43,14 @@ def _dims_struct(cfg: AsrConfig) -> _lib.AsrbDims:
 
 
 @dataclass
+class TranscribeResult:           # inference.rs:270-274
+    text: str
+    language: str
+    raw_output: str
+    ids: List[int]
+
+
+@dataclass
 class TranscribeIds:
     ids: List[List[int]]          # generated ids per utterance, EOS excluded
     stage_ms: Dict[str, float]    # device time per stage (CUDA events)
@@ -60,6 +68,7 @@ class AsrInference:
         self._session = None
         self._cap = None
         self._options: Dict[str, str] = {}
+        self.tokenizer = None     # text.AsrTokenizer when model_dir has tokenizer.json
 
     # ---- construction ------------------------------------------------------------
     @staticmethod
@@ -78,7 +87,11 @@ class AsrInference:
         d = _lib.AsrbDims()
         _lib.check(lib.asrb_model_dims(model, C.byref(d)))
         cfg = AsrConfig.from_file(os.path.join(model_dir, "config.json"))
-        return cls(cfg, ctx, model)
+        eng = cls(cfg, ctx, model)
+        if os.path.exists(os.path.join(model_dir, "tokenizer.json")):
+            from .text import AsrTokenizer
+            eng.tokenizer = AsrTokenizer.from_dir(model_dir)
+        return eng
 
     @classmethod
     def from_weights(cls, cfg: AsrConfig, weights: Dict[str, "object"], device: int = 0) -> "AsrInference":
@@ -189,6 +202,21 @@ class AsrInference:
         _lib.check(self._lib.asrb_last_timings(s, ms, C.byref(k), C.byref(st)))
         names = ("h2d", "mel", "encoder", "prefill", "decode", "total")
         return TranscribeIds([ids[b, : n[b]].tolist() for b in range(B)], dict(zip(names, ms)), k.value, st.value)
+
+    def transcribe(self, audio_path: str, language: Optional[str] = None,
+                   max_new_tokens: int = MAX_NEW_TOKENS) -> TranscribeResult:
+        """AsrInference::transcribe (inference.rs:89-213): step 1 (WAV ingest, host) -> steps 2-8 on the GPU ->
+        step 9 (detokenise + parse, host; needs tokenizer.json, else raw_output is the id list as text)."""
+        from .audio import load_wav
+        from .text import language_prompt_ids, parse_asr_output
+        samples = load_wav(audio_path, MEL_SAMPLE_RATE)
+        lang_ids = language_prompt_ids(self.tokenizer, language)
+        r = self.transcribe_ids([samples], language_ids=[lang_ids] if lang_ids is not None else None,
+                                max_new_tokens=max_new_tokens)
+        ids = r.ids[0]
+        raw = self.tokenizer.decode(ids) if self.tokenizer is not None else " ".join(str(i) for i in ids)
+        lang, text = parse_asr_output(raw, language is not None) if self.tokenizer is not None else ("unknown", raw)
+        return TranscribeResult(text=text, language=lang, raw_output=raw, ids=ids)
 
     # ---- stage-level calls (the calls transcribe() makes; used by the parity tests) ----
     def mel(self, clips: Sequence[np.ndarray], max_new_tokens: int = 64, max_lang: int = 16) -> List[np.ndarray]:

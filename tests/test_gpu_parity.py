@@ -224,3 +224,59 @@ def test_token_ids_batch_larger_than_8(tiny, tiny_engine):
     got = tiny_engine.transcribe_ids(clips, max_new_tokens=10)
     for g, c in zip(got.ids, clips):
         assert g == O.transcribe_ids(model, c, max_new_tokens=10).ids
+
+
+def test_long_generation_crosses_fused_step_limit(tiny, tiny_engine):
+    """The fused decode step covers contexts up to 640 keys; a 30 s prompt (405) + 300 new tokens crosses it
+    mid-generation and must continue seamlessly on the per-phase path (same KV cache, same state)."""
+    _, _, model = tiny
+    x = synth.make_clip(300, 30.0)
+    n_new = 300
+    ref = O.transcribe_ids(model, x, max_new_tokens=n_new)
+    got = tiny_engine.transcribe_ids([x], max_new_tokens=n_new)
+    assert len(ref.ids) == n_new
+    assert got.ids[0] == ref.ids
+    assert got.decode_steps == n_new - 1
+
+
+def test_max_new_tokens_one(tiny, tiny_engine):
+    _, _, model = tiny
+    x = synth.make_clip(301, 1.7)
+    assert tiny_engine.transcribe_ids([x], max_new_tokens=1).ids[0] == O.transcribe_ids(model, x, max_new_tokens=1).ids
+
+
+def test_transcribe_file_end_to_end(tiny, tmp_path):
+    """AsrInference::{load, transcribe} (inference.rs:30-213) through the public API: model directory with
+    config.json + safetensors + tokenizer.json, a 24 kHz stereo WAV on disk -> text.  The tokenizer is a synthetic
+    word-level vocabulary (id i <-> "t<i>") so that the decoded string identifies the generated ids."""
+    import json
+    import wave
+    from qwen3_asr_rs_b200 import AsrInference
+    from qwen3_asr_rs_b200.audio import load_wav
+    cfg, w, model = tiny
+    d = tmp_path / "model"
+    synth.write_checkpoint(str(d), cfg, w)
+    vocab = {f"t{i}": i for i in range(cfg.text.vocab_size)}
+    tok = {"version": "1.0", "truncation": None, "padding": None, "added_tokens": [], "normalizer": None,
+           "pre_tokenizer": {"type": "Whitespace"}, "post_processor": None, "decoder": None,
+           "model": {"type": "WordLevel", "vocab": vocab, "unk_token": "t0"}}
+    (d / "tokenizer.json").write_text(json.dumps(tok))
+    x24 = synth.make_clip(77, 2.0, sample_rate=24000)
+    pcm = (np.stack([x24, x24], 1) * 32767).astype("<i2")
+    wav = tmp_path / "clip.wav"
+    with wave.open(str(wav), "wb") as f:
+        f.setnchannels(2); f.setsampwidth(2); f.setframerate(24000); f.writeframes(pcm.tobytes())
+    samples = load_wav(str(wav))
+    ref = O.transcribe_ids(model, samples, max_new_tokens=8)
+    eng = AsrInference.load(str(d), device=0)
+    try:
+        r = eng.transcribe(str(wav), max_new_tokens=8)
+        forced = eng.transcribe(str(wav), language="english", max_new_tokens=8)
+    finally:
+        eng.close()
+    assert r.ids == ref.ids
+    assert r.raw_output.split() == [f"t{i}" for i in ref.ids]
+    assert r.language == "unknown"
+    # "language English" -> two unknown words -> unk id 0 twice
+    ref_forced = O.transcribe_ids(model, samples, language_ids=[0, 0], max_new_tokens=8)
+    assert forced.language == "forced" and forced.ids == ref_forced.ids
