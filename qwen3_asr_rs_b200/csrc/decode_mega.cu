@@ -182,8 +182,8 @@ struct Ring {
 struct Slice { const bf16* W; int K, r0, r1, rpc; };
 __device__ __forceinline__ Slice make_slice(const bf16* W, int N, int K, int rstep) {
     Slice s; s.W = W; s.K = K;
-    int units = N / rstep;
-    int u0 = (int)(((long long)blockIdx.x * units) / gridDim.x), u1 = (int)(((long long)(blockIdx.x + 1) * units) / gridDim.x);
+    const unsigned units = (unsigned)(N / rstep);      // units * gridDim.x < 2^32 for every matrix of the model
+    const int u0 = (int)((blockIdx.x * units) / gridDim.x), u1 = (int)(((blockIdx.x + 1) * units) / gridDim.x);
     s.r0 = u0 * rstep; s.r1 = u1 * rstep;
     s.rpc = SLOT_BYTES / (K * 2);
     s.rpc &= ~1;                        // keep (gate, up) pairs together
@@ -253,6 +253,19 @@ __device__ __forceinline__ void load_xr(const float* xs, float (&xr)[K / 32], in
         xr[c * 8 + 4] = b.x; xr[c * 8 + 5] = b.y; xr[c * 8 + 6] = b.z; xr[c * 8 + 7] = b.w;
     }
 }
+// same, with the RMSNorm applied on the fly: xr = (x * r) * w  (rounding order of layers.rs:48-54)
+template <int K>
+__device__ __forceinline__ void load_xr_norm(const float* xs, const float* wn, float r, float (&xr)[K / 32], int lane) {
+#pragma unroll
+    for (int c = 0; c < K / 256; ++c) {
+        const int o = (c * 32 + lane) * 8;
+        const float4 a = *reinterpret_cast<const float4*>(xs + o), b = *reinterpret_cast<const float4*>(xs + o + 4);
+        const float4 wa = *reinterpret_cast<const float4*>(wn + o), wb = *reinterpret_cast<const float4*>(wn + o + 4);
+        xr[c * 8 + 0] = (a.x * r) * wa.x; xr[c * 8 + 1] = (a.y * r) * wa.y; xr[c * 8 + 2] = (a.z * r) * wa.z; xr[c * 8 + 3] = (a.w * r) * wa.w;
+        xr[c * 8 + 4] = (b.x * r) * wb.x; xr[c * 8 + 5] = (b.y * r) * wb.y; xr[c * 8 + 6] = (b.z * r) * wb.z; xr[c * 8 + 7] = (b.w * r) * wb.w;
+    }
+}
+
 template <int K>
 __device__ __forceinline__ float row_dot(const uint4* wrow, const float (&xr)[K / 32], int lane) {
     float a0 = 0.f, a1 = 0.f;
@@ -291,13 +304,15 @@ enum { ME_STORE = 0, ME_RESID = 1, ME_SWIGLU = 2, ME_ARGMAX = 3 };
 // residual rows `xres` and published (ME_RESID), or folded into the running argmax (ME_ARGMAX).
 template <int K, int EPI>
 __device__ __forceinline__ void consume(const Slice& s, const Ring& ring, uint32_t& q, const float* xs, uint2* out,
-                                        uint32_t tag, float* xres, float& best_v, int& best_i) {
+                                        uint32_t tag, float* xres, float& best_v, int& best_i,
+                                        const float* norm_w = nullptr, float norm_r = 1.f) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int RSTEP = (EPI == ME_SWIGLU) ? 2 : 1;
     constexpr bool XREG = K <= 2048;               // long-K slices (down_proj, 7 rows per CTA) read x from smem instead
     float xr[XREG ? K / 32 : 1];
     if (XREG) {
-        load_xr<XREG ? K : 256>(xs, reinterpret_cast<float (&)[(XREG ? K : 256) / 32]>(xr), lane);
+        if (norm_w) load_xr_norm<XREG ? K : 256>(xs, norm_w, norm_r, reinterpret_cast<float (&)[(XREG ? K : 256) / 32]>(xr), lane);
+        else load_xr<XREG ? K : 256>(xs, reinterpret_cast<float (&)[(XREG ? K : 256) / 32]>(xr), lane);
         cons_sync();                               // every warp holds its copy: xs may be overwritten from here on
     }
     int unit = 0;                                  // unit index within this CTA's slice
@@ -333,8 +348,9 @@ __device__ __forceinline__ void consume(const Slice& s, const Ring& ring, uint32
     if (!XREG) cons_sync();                        // xs was read in place: nobody may overwrite it before this point
 }
 
-// finish an RMSNorm whose input already sits in xs (per-thread partial sum of squares `ss`)
-__device__ __forceinline__ void norm_in_smem(float ss, const float* __restrict__ w, int n, float eps, float* xs, float* red) {
+// RMSNorm scale of the vector sitting in xs from the per-thread partial sums of squares; the scaling itself is
+// fused into the register load of the GEMV (load_xr_norm).  Ends with a barrier: xs is complete for every warp.
+__device__ __forceinline__ float norm_scale(float ss, int n, float eps, float* red) {
     const int tid = threadIdx.x;
     ss = warp_sum(ss);
     if ((tid & 31) == 0) red[tid >> 5] = ss;
@@ -342,9 +358,7 @@ __device__ __forceinline__ void norm_in_smem(float ss, const float* __restrict__
     float tot = 0.f;
 #pragma unroll
     for (int i = 0; i < NCONS_WARPS; ++i) tot += red[i];
-    const float r = 1.0f / sqrtf(tot / n + eps);
-    for (int i = tid; i < n; i += NCONS) xs[i] = (xs[i] * r) * w[i];
-    cons_sync();
+    return 1.0f / sqrtf(tot / n + eps);
 }
 
 // per-head RMSNorm + RoPE of one 128-vector by one warp (lane holds d = lane, +32, +64, +96);
@@ -497,6 +511,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
 
     // residual rows owned by this CTA (same row partition for o_proj and down_proj)
     const Slice xsl = make_slice(nullptr, H, QD, 1);
+    // slice geometry does not depend on the layer: computed once, only the weight pointer changes
+    Slice sl_qkv = make_slice(nullptr, QD + 2 * p.KVD, H, 1), sl_o = make_slice(nullptr, H, QD, 1),
+          sl_gu = make_slice(nullptr, 2 * I, H, 2), sl_dn = make_slice(nullptr, H, I, 1);
     for (int i = tid; i < xsl.r1 - xsl.r0; i += NCONS) xres[i] = __ldcg(p.x + xsl.r0 + i);
 
     for (int l = 0; l < p.L; ++l) {
@@ -505,13 +522,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
         const float* pb = pbuf + (l & 1) * PARAM_FLOATS;               // ln_in | ln_post | q_norm | k_norm of this layer
         mbar_wait(&p_full[l & 1], (l >> 1) & 1);
         // ---- phase 1: RMSNorm + [q|k|v] GEMV ----
+        float nr;
         {
             float ss = 0.f;
             if (l == 0) { for (int i = tid; i < H; i += NCONS) { const float v = __ldcg(p.x + i); xs[i] = v; ss = fmaf(v, v, ss); } }
             else { count_wait(p.cnt + (l - 1) * 8 + PH_XD, epoch * G); ss = ll_gather(p.x_ll, H, (tag_base | ((uint32_t)(l - 1) << 3)) | PH_XD, xs); }
-            norm_in_smem(ss, pb, H, p.eps, xs, red);
+            nr = norm_scale(ss, H, p.eps, red);
         }
-        consume<H, ME_STORE>(make_slice(w.wqkv, QD + 2 * p.KVD, H, 1), ring, q, xs, p.qkv_ll, tl | PH_QKV, xres, best_v, best_i);
+        consume<H, ME_STORE>(sl_qkv, ring, q, xs, p.qkv_ll, tl | PH_QKV, xres, best_v, best_i, pb, nr);
         MEGA_MARK();
         // ---- phase 2: attention partials, work item = (kv head, 64-key split) ----
         {
@@ -646,7 +664,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
         count_wait(p.cnt + l * 8 + PH_ATTN, epoch * (unsigned)p.nkv);
         ll_gather(p.attn_ll, QD, tl | PH_ATTN, xs);
         cons_sync();
-        consume<QD, ME_RESID>(make_slice(w.wo, H, QD, 1), ring, q, xs, p.x_ll, tl | PH_XO, xres, best_v, best_i);
+        consume<QD, ME_RESID>(sl_o, ring, q, xs, p.x_ll, tl | PH_XO, xres, best_v, best_i);
         count_arrive(p.cnt + l * 8 + PH_XO);
         MEGA_MARK();
         // ---- phase 4: RMSNorm + gate/up GEMV + SiLU*mul ----
@@ -654,29 +672,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
         {
             count_wait(p.cnt + l * 8 + PH_XO, epoch * G);
             const float ss = ll_gather(p.x_ll, H, tl | PH_XO, xs);
-            norm_in_smem(ss, pb + H, H, p.eps, xs, red);
+            nr = norm_scale(ss, H, p.eps, red);
         }
-        consume<H, ME_SWIGLU>(make_slice(w.wgu, 2 * I, H, 2), ring, q, xs, p.act_ll, tl | PH_ACT, xres, best_v, best_i);
+        consume<H, ME_SWIGLU>(sl_gu, ring, q, xs, p.act_ll, tl | PH_ACT, xres, best_v, best_i, pb + H, nr);
         count_arrive(p.cnt + l * 8 + PH_ACT);
         MEGA_MARK();
         // ---- phase 5: down GEMV + residual ----
         count_wait(p.cnt + l * 8 + PH_ACT, epoch * G);
         ll_gather(p.act_ll, I, tl | PH_ACT, xs);
         cons_sync();
-        consume<I, ME_RESID>(make_slice(w.wdown, H, I, 1), ring, q, xs, p.x_ll, tl | PH_XD, xres, best_v, best_i);
+        consume<I, ME_RESID>(sl_dn, ring, q, xs, p.x_ll, tl | PH_XD, xres, best_v, best_i);
         count_arrive(p.cnt + l * 8 + PH_XD);
         MEGA_MARK();
         cons_sync();
         if (lane == 0) mbar_arrive(&p_empty[l & 1]);                   // this layer's parameter buffer may be refilled
     }
     // ---- final RMSNorm + tied lm_head GEMV + argmax ----
+    float nrf;
     {
         count_wait(p.cnt + (p.L - 1) * 8 + PH_XD, epoch * G);
         const float ss = ll_gather(p.x_ll, H, (tag_base | ((uint32_t)(p.L - 1) << 3)) | PH_XD, xs);
         mbar_wait(&p_full[p.L & 1], (p.L >> 1) & 1);
-        norm_in_smem(ss, pbuf + (p.L & 1) * PARAM_FLOATS, H, p.eps, xs, red);
+        nrf = norm_scale(ss, H, p.eps, red);
     }
-    consume<H, ME_ARGMAX>(make_slice(p.lm_head, p.V, H, 1), ring, q, xs, nullptr, 0u, xres, best_v, best_i);
+    consume<H, ME_ARGMAX>(make_slice(p.lm_head, p.V, H, 1), ring, q, xs, nullptr, 0u, xres, best_v, best_i,
+                          pbuf + (p.L & 1) * PARAM_FLOATS, nrf);
     MEGA_MARK();
     // every lane of a warp saw the same values: lane 0 publishes the warp's best
     cons_sync();
