@@ -94,13 +94,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
 
 // ---- tagged exchange ({fp32 value, tag} in one 64-bit word) ------------------------------------
-// Publication uses an atomic exchange: atomics are performed at L2 as soon as they are issued, whereas plain
-// or volatile stores were measured to linger for microseconds before becoming visible to other SMs, and a
-// release fence costs ~1 us (experiments/README.md).
+// Publication is a fire-and-forget 64-bit `red.max`: the tag sits in the upper 32 bits and grows monotonically for
+// every word (epoch, then layer, then phase), so the new word is always the maximum, i.e. the reduction acts as an
+// exchange.  Reductions are performed at L2 as soon as they are issued and return nothing: plain/volatile stores
+// were measured to linger for microseconds, a release fence costs ~1 us, and `atom.exch` (which returns the old
+// value) serialised each warp's publications on the atomic round trip (~1000 cycles per GEMV row).
 __device__ __forceinline__ void ll_store(uint2* p, float v, uint32_t tag) {
     const unsigned long long val = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
-    unsigned long long old;
-    asm volatile("atom.relaxed.gpu.global.exch.b64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(val) : "memory");
+    asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(p), "l"(val) : "memory");
 }
 // arrival counters: one per (layer, phase); every producing CTA adds 1 per step, so the value reached when all
 // `nprod` producers of step `epoch` have published is epoch * nprod (never reset).
@@ -383,6 +384,10 @@ __device__ __forceinline__ void head_norm_rope(const uint2* __restrict__ src, ui
     }
 }
 
+#define MEGA_FINE(k)                                                                                    \
+    do {                                                                                               \
+        if (dbg_row && tid == 0 && l == 5) dbg_row[400 + (k)] = clock64();                              \
+    } while (0)
 #define MEGA_MARK()                                                                                    \
     do {                                                                                               \
         if (dbg_row && tid == 0 && dbg_i < DBG_SLOTS) dbg_row[dbg_i++] = clock64();                    \
@@ -526,10 +531,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
         {
             float ss = 0.f;
             if (l == 0) { for (int i = tid; i < H; i += NCONS) { const float v = __ldcg(p.x + i); xs[i] = v; ss = fmaf(v, v, ss); } }
-            else { count_wait(p.cnt + (l - 1) * 8 + PH_XD, epoch * G); ss = ll_gather(p.x_ll, H, (tag_base | ((uint32_t)(l - 1) << 3)) | PH_XD, xs); }
+            else { MEGA_FINE(0); count_wait(p.cnt + (l - 1) * 8 + PH_XD, epoch * G); MEGA_FINE(1); ss = ll_gather(p.x_ll, H, (tag_base | ((uint32_t)(l - 1) << 3)) | PH_XD, xs); MEGA_FINE(2); }
             nr = norm_scale(ss, H, p.eps, red);
+            MEGA_FINE(3);
         }
         consume<H, ME_STORE>(sl_qkv, ring, q, xs, p.qkv_ll, tl | PH_QKV, xres, best_v, best_i, pb, nr);
+        MEGA_FINE(4);
         MEGA_MARK();
         // ---- phase 2: attention partials, work item = (kv head, 64-key split) ----
         {
@@ -670,19 +677,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
         // ---- phase 4: RMSNorm + gate/up GEMV + SiLU*mul ----
         cons_sync();
         {
-            count_wait(p.cnt + l * 8 + PH_XO, epoch * G);
-            const float ss = ll_gather(p.x_ll, H, tl | PH_XO, xs);
-            nr = norm_scale(ss, H, p.eps, red);
+            MEGA_FINE(8); count_wait(p.cnt + l * 8 + PH_XO, epoch * G); MEGA_FINE(9);
+            const float ss = ll_gather(p.x_ll, H, tl | PH_XO, xs); MEGA_FINE(10);
+            nr = norm_scale(ss, H, p.eps, red); MEGA_FINE(11);
         }
         consume<H, ME_SWIGLU>(sl_gu, ring, q, xs, p.act_ll, tl | PH_ACT, xres, best_v, best_i, pb + H, nr);
+        MEGA_FINE(12);
         count_arrive(p.cnt + l * 8 + PH_ACT);
+        MEGA_FINE(13);
         MEGA_MARK();
         // ---- phase 5: down GEMV + residual ----
-        count_wait(p.cnt + l * 8 + PH_ACT, epoch * G);
-        ll_gather(p.act_ll, I, tl | PH_ACT, xs);
+        MEGA_FINE(16); count_wait(p.cnt + l * 8 + PH_ACT, epoch * G); MEGA_FINE(17);
+        ll_gather(p.act_ll, I, tl | PH_ACT, xs); MEGA_FINE(18);
         cons_sync();
         consume<I, ME_RESID>(sl_dn, ring, q, xs, p.x_ll, tl | PH_XD, xres, best_v, best_i);
+        MEGA_FINE(19);
         count_arrive(p.cnt + l * 8 + PH_XD);
+        MEGA_FINE(20);
         MEGA_MARK();
         cons_sync();
         if (lane == 0) mbar_arrive(&p_empty[l & 1]);                   // this layer's parameter buffer may be refilled
@@ -820,6 +831,13 @@ void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* 
     p.cnt = reinterpret_cast<unsigned*>(w);
     p.dbg = mb.dbg;
     g_last_dbg = mb.dbg;
+    // tags must stay monotonic for red.max publication: long before the 24-bit epoch wraps, wipe the exchange buffers
+    if (mb.steps_issued && ++*mb.steps_issued >= 0xFFFF00u) {
+        ASRB_CUDA_CHECK(cudaMemsetAsync(mb.part, 0, mb.part_bytes, st));
+        const unsigned one = 1;
+        ASRB_CUDA_CHECK(cudaMemcpyAsync(mb.bar + 1, &one, sizeof(one), cudaMemcpyHostToDevice, st));
+        *mb.steps_issued = 1;
+    }
     const size_t smem = mega_smem_bytes(c.hidden_size);
     void* args[] = {(void*)&p};
     const void* fn = nullptr;

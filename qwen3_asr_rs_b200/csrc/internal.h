@@ -173,7 +173,7 @@ void launch_decode_step_phases(const Model& m, const DecodeBufs& b, int B, float
                                bool write_logits, cudaStream_t st, int64_t* launches);
 // final-norm + lm_head + argmax on arbitrary rows of a residual stream (prefill last rows);
 // also performs the greedy bookkeeping of src/inference.rs:161-170 (EOS check, append, embed)
-struct MegaBufs { unsigned* bar = nullptr; float* part = nullptr; long long* dbg = nullptr; };   // per-session state of the fused step
+struct MegaBufs { unsigned* bar = nullptr; float* part = nullptr; long long* dbg = nullptr; size_t part_bytes = 0; unsigned* steps_issued = nullptr; };   // per-session state of the fused step
 size_t decode_mega_part_floats(const Model& m);
 int decode_mega_dbg_slots();
 void launch_greedy(const Model& m, const DecodeBufs& b, int B, cudaStream_t st, int64_t* launches);

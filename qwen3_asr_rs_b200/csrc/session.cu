@@ -47,6 +47,7 @@ struct Session {
     float *kcache = nullptr, *vcache = nullptr; size_t cache_layer_stride = 0, cache_seq_stride = 0;
     DecodeBufs db{};
     MegaBufs mega{};
+    unsigned mega_steps = 1;   // host mirror of the device epoch (upper bound): see launch_decode_step_mega
     int* d_lastrow = nullptr;
     int *h_done = nullptr, *h_ids = nullptr, *h_nout = nullptr, *h_next = nullptr;
     // int-plan offsets (into d_int)
@@ -160,6 +161,8 @@ Session* session_create(Model* m, int max_batch, int64_t max_samples, int max_la
         s->mega.bar = salloc<unsigned>(s, 4, true);
         { const unsigned one = 1; ASRB_CUDA_CHECK(cudaMemcpy(s->mega.bar + 1, &one, sizeof(one), cudaMemcpyHostToDevice)); }   // epoch 1
         s->mega.part = salloc<float>(s, decode_mega_part_floats(*m), true);   // zero = tag 0 = never written
+        s->mega.part_bytes = decode_mega_part_floats(*m) * sizeof(float);
+        s->mega.steps_issued = &s->mega_steps;
         if (getenv("ASRB_MEGA_DEBUG")) s->mega.dbg = salloc<long long>(s, decode_mega_dbg_slots(), true);
         ASRB_CUDA_CHECK(cudaMallocHost(&s->h_done, Bm * sizeof(int)));
         ASRB_CUDA_CHECK(cudaMallocHost(&s->h_nout, Bm * sizeof(int)));

@@ -31,4 +31,10 @@ for cta, row in zip(("cta0", "ctaLast"), t):
     for i, nm in enumerate(names):
         print(f"    {nm:10s} mean {per[:, i].mean():9.0f}  min {per[:, i].min():7d}  max {per[:, i].max():7d}")
     print("  layer totals (first 4):", per.sum(1)[:4])
+for cta, row in zip(("cta0", "ctaLast"), t):
+    f = row[400:424].astype(np.int64)
+    d = lambda a, b: int(f[a] - f[b])
+    print(cta, "layer-5 detail (cycles): P1 wait", d(1, 0), "gather", d(2, 1), "norm", d(3, 2), "gemv", d(4, 3),
+          "| P4 wait", d(9, 8), "gather", d(10, 9), "norm", d(11, 10), "gemv", d(12, 11), "arrive", d(13, 12),
+          "| P5 wait", d(17, 16), "gather", d(18, 17), "gemv", d(19, 18), "arrive", d(20, 19))
 eng.close()
