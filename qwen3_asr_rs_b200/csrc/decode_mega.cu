@@ -13,9 +13,10 @@
 //   * 8 consumer warps do the fp32 GEMV from shared memory (activation vector held in registers,
 //     bf16 -> fp32 up-cast is exact, fp32 FMA accumulate).
 //   * activations are exchanged between CTAs WITHOUT barriers: every published fp32 value travels
-//     in an 8-byte {value, tag} word (tag = position/layer/phase), written with one 64-bit store and
-//     polled with 128-bit volatile loads until the tags match -- data and "ready" flag arrive in the
-//     same L2 round trip (the low-latency protocol of collective libraries, applied on-chip).
+//     in an 8-byte {value, tag} word (tag = launch epoch/layer/phase), published with one 64-bit
+//     fire-and-forget `red.max` (performed at L2 immediately; the tag grows monotonically so max acts as
+//     an exchange) and polled with 128-bit relaxed loads until the tags match -- data and "ready" flag
+//     arrive in the same L2 round trip (the low-latency protocol of collective libraries, on-chip).
 //   * attention (QK-RMSNorm + RoPE + KV append + softmax.V) is split over kv-heads x 64-key tiles;
 //     the tile-0 CTA of each kv-head merges the partials and publishes the head outputs.
 //   * the last CTA to finish the lm_head performs the greedy bookkeeping (argmax, EOS, append,
@@ -30,8 +31,8 @@ namespace mega {
 static constexpr int NCONS_WARPS = 8;
 static constexpr int NCONS = NCONS_WARPS * 32;          // 256 consumer threads
 static constexpr int NTHREADS = NCONS + 32;             // + 1 producer warp
-static constexpr int SLOT_BYTES = 24 * 1024;
-static constexpr int NSLOT = 5;                         // weight ring: 120 KB in flight per SM
+static constexpr int SLOT_BYTES = 32 * 1024;           // 16 rows of K = 1024: one row per half-warp and pass
+static constexpr int NSLOT = 4;                         // weight ring: 128 KB in flight per SM
 static constexpr int KV_KEYS = 64;                      // keys per attention split (K and V tiles staged in smem)
 static constexpr int KV_TILE_BYTES = KV_KEYS * 128 * 4; // 32 KB each for K and V (fp32 cache)
 static constexpr int XS_FLOATS = 3072 + 64;             // activation vector / attention scratch
@@ -61,7 +62,6 @@ struct Params {
     unsigned* bar;               // [0] finish ticket, [1] launch epoch (starts at 1; 0 marks never-written words)
     // tagged exchange buffers ({value, tag} words)
     uint2* qkv_ll; uint2* part_ll; uint2* attn_ll; uint2* x_ll; uint2* act_ll;
-    unsigned* cnt;               // [L + 1][8] arrival counters
     long long* dbg;              // optional timeline [2][DBG_SLOTS] of clock64 (CTA 0 and CTA G-1), else null
 };
 
@@ -103,19 +103,6 @@ __device__ __forceinline__ void ll_store(uint2* p, float v, uint32_t tag) {
     const unsigned long long val = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
     asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(p), "l"(val) : "memory");
 }
-// arrival counters: one per (layer, phase); every producing CTA adds 1 per step, so the value reached when all
-// `nprod` producers of step `epoch` have published is epoch * nprod (never reset).
-__device__ __forceinline__ void count_arrive(unsigned* c) {
-    cons_sync();                                   // all warps of this CTA have issued their publications
-    if (threadIdx.x == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(c) : "memory");
-}
-__device__ __forceinline__ void count_wait(const unsigned* c, unsigned target) {
-    if (threadIdx.x == 0) {
-        unsigned v;
-        do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory"); } while ((int)(v - target) < 0);
-    }
-    cons_sync();
-}
 __device__ __forceinline__ uint4 ll_load2(const uint2* p) {      // two consecutive words (16-byte aligned)
     uint4 v;
     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -141,6 +128,10 @@ __device__ __forceinline__ void ll_poll4(const uint2* p, int stride, uint32_t ta
 #pragma unroll
     for (int i = 0; i < 4; ++i) out[i] = __uint_as_float(v[i].x);
 }
+// Activation vectors in shared memory are stored with 16-byte group k at k ^ ((k >> 3) & 1).  The GEMV register loads
+// read, per lane, the two groups of 8 consecutive elements (32-byte lane stride): unswizzled, lanes i and i+4 of every
+// quarter warp hit the same banks (2-way conflict on every LDS.128, ~1000 cycles per phase for 8 warps x 8 KB).
+__device__ __forceinline__ int xs_swz(int e) { const int k = e >> 2; return ((k ^ ((k >> 3) & 1)) << 2) | (e & 3); }
 // all consumer threads: gather n (even) tagged values into shared memory; returns this thread's sum of squares
 __device__ __forceinline__ float ll_gather(const uint2* buf, int n, uint32_t tag, float* xs) {
     float ss = 0.f;
@@ -167,7 +158,7 @@ __device__ __forceinline__ float ll_gather(const uint2* buf, int n, uint32_t tag
             const int i = i0 + u * NCONS;
             if (i < pairs) {
                 const float a = __uint_as_float(v[u].x), b = __uint_as_float(v[u].z);
-                xs[2 * i] = a; xs[2 * i + 1] = b;
+                *reinterpret_cast<float2*>(xs + xs_swz(2 * i)) = make_float2(a, b);
                 ss = fmaf(a, a, ss); ss = fmaf(b, b, ss);
             }
         }
@@ -244,12 +235,15 @@ __device__ __forceinline__ void produce(const Slice& s, const Ring& ring, uint32
     }
 }
 
+// GEMV row mapping: a row of K bf16 weights is contracted by one warp; lane `lane` holds the activations of elements
+// (c * 32 + lane) * 8 .. +8 for every 256-element chunk c in registers.
 template <int K>
 __device__ __forceinline__ void load_xr(const float* xs, float (&xr)[K / 32], int lane) {
 #pragma unroll
+    const int sw = ((lane >> 2) & 1) * 4;          // xs_swz for this lane's two 16-byte groups: swapped when bit 3 of k is set
     for (int c = 0; c < K / 256; ++c) {
-        const float4 a = *reinterpret_cast<const float4*>(xs + (c * 32 + lane) * 8);
-        const float4 b = *reinterpret_cast<const float4*>(xs + (c * 32 + lane) * 8 + 4);
+        const float4 a = *reinterpret_cast<const float4*>(xs + (c * 32 + lane) * 8 + sw);
+        const float4 b = *reinterpret_cast<const float4*>(xs + (c * 32 + lane) * 8 + 4 - sw);
         xr[c * 8 + 0] = a.x; xr[c * 8 + 1] = a.y; xr[c * 8 + 2] = a.z; xr[c * 8 + 3] = a.w;
         xr[c * 8 + 4] = b.x; xr[c * 8 + 5] = b.y; xr[c * 8 + 6] = b.z; xr[c * 8 + 7] = b.w;
     }
@@ -258,10 +252,11 @@ __device__ __forceinline__ void load_xr(const float* xs, float (&xr)[K / 32], in
 template <int K>
 __device__ __forceinline__ void load_xr_norm(const float* xs, const float* wn, float r, float (&xr)[K / 32], int lane) {
 #pragma unroll
+    const int sw = ((lane >> 2) & 1) * 4;          // both vectors are stored in the xs_swz layout
     for (int c = 0; c < K / 256; ++c) {
         const int o = (c * 32 + lane) * 8;
-        const float4 a = *reinterpret_cast<const float4*>(xs + o), b = *reinterpret_cast<const float4*>(xs + o + 4);
-        const float4 wa = *reinterpret_cast<const float4*>(wn + o), wb = *reinterpret_cast<const float4*>(wn + o + 4);
+        const float4 a = *reinterpret_cast<const float4*>(xs + o + sw), b = *reinterpret_cast<const float4*>(xs + o + 4 - sw);
+        const float4 wa = *reinterpret_cast<const float4*>(wn + o + sw), wb = *reinterpret_cast<const float4*>(wn + o + 4 - sw);
         xr[c * 8 + 0] = (a.x * r) * wa.x; xr[c * 8 + 1] = (a.y * r) * wa.y; xr[c * 8 + 2] = (a.z * r) * wa.z; xr[c * 8 + 3] = (a.w * r) * wa.w;
         xr[c * 8 + 4] = (b.x * r) * wb.x; xr[c * 8 + 5] = (b.y * r) * wb.y; xr[c * 8 + 6] = (b.z * r) * wb.z; xr[c * 8 + 7] = (b.w * r) * wb.w;
     }
@@ -280,16 +275,41 @@ __device__ __forceinline__ float row_dot(const uint4* wrow, const float (&xr)[K 
     }
     return warp_sum(a0 + a1);
 }
+// two rows at once (independent FMA chains, one shared reduction): the result of row 0 ends up in lanes 0-15 and
+// that of row 1 in lanes 16-31
+template <int K>
+__device__ __forceinline__ float row_dot2(const uint4* w0, const uint4* w1, const float (&xr)[K / 32], int lane) {
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < K / 256; ++c) {
+        const uint4 w = w0[c * 32 + lane], v = w1[c * 32 + lane];
+        a0 = fmaf(bf16_lo(w.x), xr[c * 8 + 0], a0); a1 = fmaf(bf16_hi(w.x), xr[c * 8 + 1], a1);
+        b0 = fmaf(bf16_lo(v.x), xr[c * 8 + 0], b0); b1 = fmaf(bf16_hi(v.x), xr[c * 8 + 1], b1);
+        a0 = fmaf(bf16_lo(w.y), xr[c * 8 + 2], a0); a1 = fmaf(bf16_hi(w.y), xr[c * 8 + 3], a1);
+        b0 = fmaf(bf16_lo(v.y), xr[c * 8 + 2], b0); b1 = fmaf(bf16_hi(v.y), xr[c * 8 + 3], b1);
+        a0 = fmaf(bf16_lo(w.z), xr[c * 8 + 4], a0); a1 = fmaf(bf16_hi(w.z), xr[c * 8 + 5], a1);
+        b0 = fmaf(bf16_lo(v.z), xr[c * 8 + 4], b0); b1 = fmaf(bf16_hi(v.z), xr[c * 8 + 5], b1);
+        a0 = fmaf(bf16_lo(w.w), xr[c * 8 + 6], a0); a1 = fmaf(bf16_hi(w.w), xr[c * 8 + 7], a1);
+        b0 = fmaf(bf16_lo(v.w), xr[c * 8 + 6], b0); b1 = fmaf(bf16_hi(v.w), xr[c * 8 + 7], b1);
+    }
+    const float ra = a0 + a1, rb = b0 + b1;
+    const bool hi = lane & 16;
+    float keep = (hi ? rb : ra) + __shfl_xor_sync(0xffffffffu, hi ? ra : rb, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    return keep;
+}
 
 // same contraction with the activation vector read from shared memory (long K: keeps registers free)
 template <int K>
 __device__ __forceinline__ float row_dot_smem(const uint4* wrow, const float* xs, int lane) {
     float a0 = 0.f, a1 = 0.f;
+    const int sw = ((lane >> 2) & 1) * 4;
 #pragma unroll 4
     for (int c = 0; c < K / 256; ++c) {
         const uint4 w = wrow[c * 32 + lane];
-        const float4 xa = *reinterpret_cast<const float4*>(xs + (c * 32 + lane) * 8);
-        const float4 xb = *reinterpret_cast<const float4*>(xs + (c * 32 + lane) * 8 + 4);
+        const float4 xa = *reinterpret_cast<const float4*>(xs + (c * 32 + lane) * 8 + sw);
+        const float4 xb = *reinterpret_cast<const float4*>(xs + (c * 32 + lane) * 8 + 4 - sw);
         a0 = fmaf(bf16_lo(w.x), xa.x, a0); a1 = fmaf(bf16_hi(w.x), xa.y, a1);
         a0 = fmaf(bf16_lo(w.y), xa.z, a0); a1 = fmaf(bf16_hi(w.y), xa.w, a1);
         a0 = fmaf(bf16_lo(w.z), xb.x, a0); a1 = fmaf(bf16_hi(w.z), xb.y, a1);
@@ -306,46 +326,79 @@ enum { ME_STORE = 0, ME_RESID = 1, ME_SWIGLU = 2, ME_ARGMAX = 3 };
 template <int K, int EPI>
 __device__ __forceinline__ void consume(const Slice& s, const Ring& ring, uint32_t& q, const float* xs, uint2* out,
                                         uint32_t tag, float* xres, float& best_v, int& best_i,
-                                        const float* norm_w = nullptr, float norm_r = 1.f) {
+                                        const float* norm_w = nullptr, float norm_r = 1.f, long long* fine = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int fi = 0;
+#define CF() do { if (fine && threadIdx.x == 0 && fi < 24) fine[fi++] = clock64(); } while (0)
+    CF();
     constexpr int RSTEP = (EPI == ME_SWIGLU) ? 2 : 1;
     constexpr bool XREG = K <= 2048;               // long-K slices (down_proj, 7 rows per CTA) read x from smem instead
+    constexpr bool DUAL = XREG && K <= 1024;       // two rows per warp and turn: a 16-row slot is one pass of the 8 warps
+    constexpr int KX = XREG ? K : 256;             // dummy instantiation size when x stays in smem
+    constexpr int UPW = (DUAL && EPI != ME_SWIGLU) ? 2 : 1;       // units (rows or pairs) a warp takes per turn
+    const int sub = lane >> 4;
     float xr[XREG ? K / 32 : 1];
     if (XREG) {
-        if (norm_w) load_xr_norm<XREG ? K : 256>(xs, norm_w, norm_r, reinterpret_cast<float (&)[(XREG ? K : 256) / 32]>(xr), lane);
-        else load_xr<XREG ? K : 256>(xs, reinterpret_cast<float (&)[(XREG ? K : 256) / 32]>(xr), lane);
+        if (norm_w) load_xr_norm<KX>(xs, norm_w, norm_r, reinterpret_cast<float (&)[KX / 32]>(xr), lane);
+        else load_xr<KX>(xs, reinterpret_cast<float (&)[KX / 32]>(xr), lane);
         cons_sync();                               // every warp holds its copy: xs may be overwritten from here on
     }
-    int unit = 0;                                  // unit index within this CTA's slice
+    CF();
+    int unit = 0;                                  // unit index within this CTA's slice (kept a multiple of UPW per slot)
     for (int r = s.r0; r < s.r1; r += s.rpc, ++q) {
         const int rows = min(s.rpc, s.r1 - r);
         const uint32_t slot = q % NSLOT, par = (q / NSLOT) & 1;
         mbar_wait(&ring.full[slot], par);
+        CF();
         const uint4* base = reinterpret_cast<const uint4*>(ring.slots + (size_t)slot * SLOT_BYTES);
         const int units_here = rows / RSTEP;
-        // units are dealt round-robin to warps across the whole slice
-        int first = (warp - (unit % NCONS_WARPS) + NCONS_WARPS) % NCONS_WARPS;
-        for (int u = first; u < units_here; u += NCONS_WARPS) {
-            const int row = r + u * RSTEP;
-            float v0, v1 = 0.f;
-            if (XREG) v0 = row_dot<XREG ? K : 256>(base + (size_t)(u * RSTEP) * (K / 8), reinterpret_cast<const float (&)[(XREG ? K : 256) / 32]>(xr), lane);
-            else v0 = row_dot_smem<K>(base + (size_t)(u * RSTEP) * (K / 8), xs, lane);
+        // units are dealt round-robin to warps across the whole slice (UPW consecutive units per warp and turn)
+        const int first = (warp - ((unit / UPW) % NCONS_WARPS) + NCONS_WARPS) % NCONS_WARPS;
+        for (int ub = first * UPW; ub < units_here; ub += NCONS_WARPS * UPW) {
             if (EPI == ME_SWIGLU) {
-                if (XREG) v1 = row_dot<XREG ? K : 256>(base + (size_t)(u * RSTEP + 1) * (K / 8), reinterpret_cast<const float (&)[(XREG ? K : 256) / 32]>(xr), lane);
-                else v1 = row_dot_smem<K>(base + (size_t)(u * RSTEP + 1) * (K / 8), xs, lane);
+                const int row = r + ub * 2;        // gate row; up row = row + 1
+                float v0, v1;
+                if (DUAL) {
+                    const float v = row_dot2<KX>(base + (size_t)(ub * 2) * (K / 8), base + (size_t)(ub * 2 + 1) * (K / 8),
+                                                 reinterpret_cast<const float (&)[KX / 32]>(xr), lane);
+                    v0 = v; v1 = __shfl_xor_sync(0xffffffffu, v, 16);      // valid on the lower half (lane 0 publishes)
+                } else if (XREG) {
+                    v0 = row_dot<KX>(base + (size_t)(ub * 2) * (K / 8), reinterpret_cast<const float (&)[KX / 32]>(xr), lane);
+                    v1 = row_dot<KX>(base + (size_t)(ub * 2 + 1) * (K / 8), reinterpret_cast<const float (&)[KX / 32]>(xr), lane);
+                } else {
+                    v0 = row_dot_smem<K>(base + (size_t)(ub * 2) * (K / 8), xs, lane);
+                    v1 = row_dot_smem<K>(base + (size_t)(ub * 2 + 1) * (K / 8), xs, lane);
+                }
                 if (lane == 0) ll_store(out + (row >> 1), silu(v0) * v1, tag);
-            } else if (EPI == ME_STORE) {
-                if (lane == 0) ll_store(out + row, v0, tag);
-            } else if (EPI == ME_RESID) {
-                if (lane == 0) { const float nv = xres[row - s.r0] + v0; xres[row - s.r0] = nv; ll_store(out + row, nv, tag); }
             } else {
-                if (v0 > best_v) { best_v = v0; best_i = row; }
+                bool act; int row; float v0;
+                if (DUAL) {
+                    const bool two = ub + 1 < units_here;                 // the slot's last turn may hold a single row
+                    v0 = row_dot2<KX>(base + (size_t)ub * (K / 8), base + (size_t)(two ? ub + 1 : ub) * (K / 8),
+                                      reinterpret_cast<const float (&)[KX / 32]>(xr), lane);
+                    act = ((lane & 15) == 0) && (sub == 0 || two);
+                    row = r + ub + sub;
+                } else {
+                    if (XREG) v0 = row_dot<KX>(base + (size_t)ub * (K / 8), reinterpret_cast<const float (&)[KX / 32]>(xr), lane);
+                    else v0 = row_dot_smem<K>(base + (size_t)ub * (K / 8), xs, lane);
+                    act = lane == 0; row = r + ub;
+                }
+                if (EPI == ME_STORE) {
+                    if (act) ll_store(out + row, v0, tag);
+                } else if (EPI == ME_RESID) {
+                    if (act) { const float nv = xres[row - s.r0] + v0; xres[row - s.r0] = nv; ll_store(out + row, nv, tag); }
+                } else {
+                    if (act && v0 > best_v) { best_v = v0; best_i = row; }
+                }
             }
         }
-        unit += units_here;
+        unit += (units_here + UPW - 1) / UPW * UPW;
+        CF();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ring.empty[slot]);
     }
+    CF();
+#undef CF
     if (!XREG) cons_sync();                        // xs was read in place: nobody may overwrite it before this point
 }
 
@@ -395,7 +448,7 @@ __device__ __forceinline__ void head_norm_rope(const uint2* __restrict__ src, ui
 
 template <int H, int QD, int I>
 __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     constexpr int PARAM_FLOATS = 2 * H + 2 * HD;      // per-layer small vectors: ln_in[H], ln_post[H], q_norm[128], k_norm[128]
     Ring ring;
     ring.slots = smem;
@@ -513,7 +566,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     // tag = launch epoch (unique per executed step, survives new utterances that revisit the same positions)
     const unsigned epoch = __ldcg(p.bar + 1);
     const uint32_t tag_base = (epoch & 0xffffffu) << 8;
-
     // residual rows owned by this CTA (same row partition for o_proj and down_proj)
     const Slice xsl = make_slice(nullptr, H, QD, 1);
     // slice geometry does not depend on the layer: computed once, only the weight pointer changes
@@ -530,8 +582,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
         float nr;
         {
             float ss = 0.f;
-            if (l == 0) { for (int i = tid; i < H; i += NCONS) { const float v = __ldcg(p.x + i); xs[i] = v; ss = fmaf(v, v, ss); } }
-            else { MEGA_FINE(0); count_wait(p.cnt + (l - 1) * 8 + PH_XD, epoch * G); MEGA_FINE(1); ss = ll_gather(p.x_ll, H, (tag_base | ((uint32_t)(l - 1) << 3)) | PH_XD, xs); MEGA_FINE(2); }
+            if (l == 0) { for (int i = tid; i < H; i += NCONS) { const float v = __ldcg(p.x + i); xs[xs_swz(i)] = v; ss = fmaf(v, v, ss); } }
+            else { MEGA_FINE(0); MEGA_FINE(1); ss = ll_gather(p.x_ll, H, (tag_base | ((uint32_t)(l - 1) << 3)) | PH_XD, xs); MEGA_FINE(2); }
             nr = norm_scale(ss, H, p.eps, red);
             MEGA_FINE(3);
         }
@@ -550,6 +602,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                 float* vn = kn + HD;                  // [128]
                 float* sc = vn + HD;                  // [group][KV_KEYS]
                 float* ml = sc + p.group * KV_KEYS;   // [group][2] (max, sum)
+                float* osum = ml + 8;                 // [warps][2][128] per-warp partial outputs (group == 2 path)
                 float* Ks = reinterpret_cast<float*>(kv_smem);
                 float* Vs = reinterpret_cast<float*>(kv_smem + KV_TILE_BYTES);
                 const bool has_new = (pos >= att_j0) && (pos < att_j0 + KV_KEYS);
@@ -573,19 +626,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                     Ks[(pos - att_j0) * HD + tid] = kx; Vs[(pos - att_j0) * HD + tid] = vx;
                 }
                 cons_sync();
-                // scores: one thread per (head, key); the d loop is rotated by the key index so that the
-                // 32 lanes of a warp hit 32 different banks of the row-major K tile
-                for (int idx = tid; idx < p.group * KV_KEYS; idx += NCONS) {
-                    const int hq = idx / KV_KEYS, j = idx - hq * KV_KEYS;
-                    if (j < nloc) {
-                        const float* kr = Ks + j * HD; const float* qr = qs + hq * HD;
-                        float a0 = 0.f, a1 = 0.f;
-#pragma unroll 8
-                        for (int dd = 0; dd < HD; dd += 2) {
-                            const int d0 = (dd + j) & (HD - 1), d1 = (dd + 1 + j) & (HD - 1);
-                            a0 = fmaf(kr[d0], qr[d0], a0); a1 = fmaf(kr[d1], qr[d1], a1);
+                if (p.group == 2) {
+                    // scores, 2 query heads per kv head: warp w takes keys w, w+8, ...; every lane multiplies its 4 dims of the
+                    // K row (one conflict-free LDS.128) with both q vectors held in registers; the 16 partial sums per lane
+                    // (8 keys x 2 heads) are reduced across the warp with a transposing butterfly (16 shuffles instead of 80)
+                    const float4 q0 = *reinterpret_cast<const float4*>(qs + lane * 4);
+                    const float4 q1 = *reinterpret_cast<const float4*>(qs + HD + lane * 4);
+                    float pv[16];
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const int j = warp + 8 * kk;
+                        float s0 = 0.f, s1 = 0.f;
+                        if (j < nloc) {
+                            const float4 kv = *reinterpret_cast<const float4*>(Ks + j * HD + lane * 4);
+                            s0 = fmaf(kv.x, q0.x, fmaf(kv.y, q0.y, fmaf(kv.z, q0.z, kv.w * q0.w)));
+                            s1 = fmaf(kv.x, q1.x, fmaf(kv.y, q1.y, fmaf(kv.z, q1.z, kv.w * q1.w)));
                         }
-                        sc[hq * KV_KEYS + j] = (a0 + a1) / sqrtf((float)HD);
+                        pv[2 * kk] = s0; pv[2 * kk + 1] = s1;
+                    }
+#pragma unroll
+                    for (int o = 16, n = 16; n > 1; o >>= 1, n >>= 1) {
+                        const bool up = lane & o;
+#pragma unroll
+                        for (int i = 0; i < n / 2; ++i) {
+                            const float send = up ? pv[i] : pv[i + n / 2];
+                            const float keep = up ? pv[i + n / 2] : pv[i];
+                            pv[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                        }
+                    }
+                    pv[0] += __shfl_xor_sync(0xffffffffu, pv[0], 1);
+                    {   // lane holds value index (lane >> 1) = kk * 2 + head
+                        const int vi = lane >> 1, j = warp + 8 * (vi >> 1);
+                        if (!(lane & 1) && j < nloc) sc[(vi & 1) * KV_KEYS + j] = pv[0] / sqrtf((float)HD);
+                    }
+                } else {
+                    // generic group size: one thread per (head, key); the d loop is rotated by the key index so that the
+                    // 32 lanes of a warp hit 32 different banks of the row-major K tile
+                    for (int idx = tid; idx < p.group * KV_KEYS; idx += NCONS) {
+                        const int hq = idx / KV_KEYS, j = idx - hq * KV_KEYS;
+                        if (j < nloc) {
+                            const float* kr = Ks + j * HD; const float* qr = qs + hq * HD;
+                            float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+                            for (int dd = 0; dd < HD; dd += 2) {
+                                const int d0 = (dd + j) & (HD - 1), d1 = (dd + 1 + j) & (HD - 1);
+                                a0 = fmaf(kr[d0], qr[d0], a0); a1 = fmaf(kr[d1], qr[d1], a1);
+                            }
+                            sc[hq * KV_KEYS + j] = (a0 + a1) / sqrtf((float)HD);
+                        }
                     }
                 }
                 cons_sync();
@@ -602,14 +690,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                     if (lane == 0) { ml[warp * 2] = mx; ml[warp * 2 + 1] = sum; }
                 }
                 cons_sync();
-                // o[hq][d] = sum_j e[hq][j] * V[j][d]; thread = (head, d); publish the partial record
-                for (int idx = tid; idx < p.group * HD; idx += NCONS) {
-                    const int hq = idx / HD, d = idx - hq * HD;
-                    float acc = 0.f;
-                    for (int j = 0; j < nloc; ++j) acc = fmaf(sc[hq * KV_KEYS + j], Vs[j * HD + d], acc);
-                    uint2* rec = p.part_ll + ((size_t)blockIdx.x * p.group + hq) * PSTRIDE;
-                    ll_store(rec + d, acc, tl | PH_PART);
-                    if (d < 2) ll_store(rec + HD + d, ml[hq * 2 + d], tl | PH_PART);
+                // o[hq][d] = sum_j e[hq][j] * V[j][d]; publish the partial record
+                if (p.group == 2) {
+                    // warp w accumulates keys w, w+8, ... for 4 dims per lane (one LDS.128 of V per key) and both heads;
+                    // the 8 per-warp partial vectors are then summed through shared memory by thread = (head, d)
+                    float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const int j = warp + 8 * kk;
+                        if (j < nloc) {
+                            const float4 vv = *reinterpret_cast<const float4*>(Vs + j * HD + lane * 4);
+                            const float e0 = sc[j], e1 = sc[KV_KEYS + j];
+                            o0.x = fmaf(e0, vv.x, o0.x); o0.y = fmaf(e0, vv.y, o0.y); o0.z = fmaf(e0, vv.z, o0.z); o0.w = fmaf(e0, vv.w, o0.w);
+                            o1.x = fmaf(e1, vv.x, o1.x); o1.y = fmaf(e1, vv.y, o1.y); o1.z = fmaf(e1, vv.z, o1.z); o1.w = fmaf(e1, vv.w, o1.w);
+                        }
+                    }
+                    *reinterpret_cast<float4*>(osum + (warp * 2 + 0) * HD + lane * 4) = o0;
+                    *reinterpret_cast<float4*>(osum + (warp * 2 + 1) * HD + lane * 4) = o1;
+                    cons_sync();
+                    {
+                        const int hq = tid / HD, d = tid - hq * HD;      // NCONS == 2 * HD
+                        float acc = 0.f;
+#pragma unroll
+                        for (int w8 = 0; w8 < NCONS_WARPS; ++w8) acc += osum[(w8 * 2 + hq) * HD + d];
+                        uint2* rec = p.part_ll + ((size_t)blockIdx.x * 2 + hq) * PSTRIDE;
+                        ll_store(rec + d, acc, tl | PH_PART);
+                        if (d < 2) ll_store(rec + HD + d, ml[hq * 2 + d], tl | PH_PART);
+                    }
+                } else {
+                    for (int idx = tid; idx < p.group * HD; idx += NCONS) {
+                        const int hq = idx / HD, d = idx - hq * HD;
+                        float acc = 0.f;
+                        for (int j = 0; j < nloc; ++j) acc = fmaf(sc[hq * KV_KEYS + j], Vs[j * HD + d], acc);
+                        uint2* rec = p.part_ll + ((size_t)blockIdx.x * p.group + hq) * PSTRIDE;
+                        ll_store(rec + d, acc, tl | PH_PART);
+                        if (d < 2) ll_store(rec + HD + d, ml[hq * 2 + d], tl | PH_PART);
+                    }
                 }
                 if (n_old > 0) {                      // hand the K/V staging buffer back to the producer
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -661,38 +777,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                         }
                         ll_store(p.attn_ll + (size_t)(g * p.group + hq) * HD + d, O / Lsum, tl | PH_ATTN);
                     }
-                    count_arrive(p.cnt + l * 8 + PH_ATTN);
                 }
                 cons_sync();                          // attention scratch (aliases xs) is free again
             }
         }
         MEGA_MARK();
         // ---- phase 3: o_proj GEMV + residual ----
-        count_wait(p.cnt + l * 8 + PH_ATTN, epoch * (unsigned)p.nkv);
         ll_gather(p.attn_ll, QD, tl | PH_ATTN, xs);
         cons_sync();
         consume<QD, ME_RESID>(sl_o, ring, q, xs, p.x_ll, tl | PH_XO, xres, best_v, best_i);
-        count_arrive(p.cnt + l * 8 + PH_XO);
         MEGA_MARK();
         // ---- phase 4: RMSNorm + gate/up GEMV + SiLU*mul ----
         cons_sync();
         {
-            MEGA_FINE(8); count_wait(p.cnt + l * 8 + PH_XO, epoch * G); MEGA_FINE(9);
+            MEGA_FINE(8); MEGA_FINE(9);
             const float ss = ll_gather(p.x_ll, H, tl | PH_XO, xs); MEGA_FINE(10);
             nr = norm_scale(ss, H, p.eps, red); MEGA_FINE(11);
         }
-        consume<H, ME_SWIGLU>(sl_gu, ring, q, xs, p.act_ll, tl | PH_ACT, xres, best_v, best_i, pb + H, nr);
+        consume<H, ME_SWIGLU>(sl_gu, ring, q, xs, p.act_ll, tl | PH_ACT, xres, best_v, best_i, pb + H, nr, (dbg_row && l == 5) ? dbg_row + 440 : nullptr);
         MEGA_FINE(12);
-        count_arrive(p.cnt + l * 8 + PH_ACT);
         MEGA_FINE(13);
         MEGA_MARK();
         // ---- phase 5: down GEMV + residual ----
-        MEGA_FINE(16); count_wait(p.cnt + l * 8 + PH_ACT, epoch * G); MEGA_FINE(17);
+        MEGA_FINE(16); MEGA_FINE(17);
         ll_gather(p.act_ll, I, tl | PH_ACT, xs); MEGA_FINE(18);
         cons_sync();
         consume<I, ME_RESID>(sl_dn, ring, q, xs, p.x_ll, tl | PH_XD, xres, best_v, best_i);
         MEGA_FINE(19);
-        count_arrive(p.cnt + l * 8 + PH_XD);
         MEGA_FINE(20);
         MEGA_MARK();
         cons_sync();
@@ -701,7 +812,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     // ---- final RMSNorm + tied lm_head GEMV + argmax ----
     float nrf;
     {
-        count_wait(p.cnt + (p.L - 1) * 8 + PH_XD, epoch * G);
         const float ss = ll_gather(p.x_ll, H, (tag_base | ((uint32_t)(p.L - 1) << 3)) | PH_XD, xs);
         mbar_wait(&p_full[p.L & 1], (p.L >> 1) & 1);
         nrf = norm_scale(ss, H, p.eps, red);
@@ -709,11 +819,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     consume<H, ME_ARGMAX>(make_slice(p.lm_head, p.V, H, 1), ring, q, xs, nullptr, 0u, xres, best_v, best_i,
                           pbuf + (p.L & 1) * PARAM_FLOATS, nrf);
     MEGA_MARK();
-    // every lane of a warp saw the same values: lane 0 publishes the warp's best
+    // candidates live in lanes 0 and 16 of every warp (row 0 / row 1 of a turn): merge them, lane 0 publishes the warp's best
+    {
+        const float ov = __shfl_xor_sync(0xffffffffu, best_v, 16); const int oi = __shfl_xor_sync(0xffffffffu, best_i, 16);
+        if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+    }
     cons_sync();
     if (lane == 0) { red[warp] = best_v; ired[warp] = best_i; }
     cons_sync();
-    __shared__ int is_last;
+    int& is_last = ired[63];
     if (tid == 0) {
         float v = -INFINITY; int idx = 0x7fffffff;
         for (int wq = 0; wq < NCONS_WARPS; ++wq)
@@ -740,7 +854,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
         }
         if (lane == 0) { red[warp] = v; ired[warp] = idx; }
         cons_sync();
-        __shared__ int tok_s;
+        int& tok_s = ired[62];
         if (tid == 0) {
             for (int wq = 1; wq < NCONS_WARPS; ++wq)
                 if (red[wq] > v || (red[wq] == v && ired[wq] < idx)) { v = red[wq]; idx = ired[wq]; }
@@ -783,7 +897,7 @@ bool decode_mega_supported(const Model& m, int B, int ctx) {
     if (B != 1 || c.head_dim != 128) return false;
     const int group = c.num_attention_heads / c.num_key_value_heads;
     if (group + 2 > mega::NCONS_WARPS) return false;
-    if ((size_t)(group * 128 + 256 + group * mega::KV_KEYS + group * 2) > (size_t)mega::XS_FLOATS) return false;
+    if ((size_t)(group * 128 + 256 + group * mega::KV_KEYS + 8 + mega::NCONS_WARPS * 2 * 128) > (size_t)mega::XS_FLOATS) return false;
     if (m.ctx->smem_optin < mega_smem_bytes()) return false;
     if ((c.hidden_size + m.ctx->sm_count - 1) / m.ctx->sm_count + 1 > mega::XRES_MAX) return false;
     if (c.num_hidden_layers > 32) return false;                  // 5-bit layer field
@@ -798,7 +912,7 @@ size_t decode_mega_part_floats(const Model& m) {
     const int group = c.num_attention_heads / c.num_key_value_heads;
     const size_t words = (size_t)m.d.qkv_dim + (size_t)m.ctx->sm_count * group * mega::PSTRIDE + m.d.q_dim + c.hidden_size +
                          c.intermediate_size + 64;
-    return 2 * words + (size_t)(c.num_hidden_layers + 1) * 8 + 64;     // tagged words + arrival counters
+    return 2 * words + 64;
 }
 
 void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* kcache, float* vcache,
@@ -813,7 +927,7 @@ void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* 
     // split count is fixed per session (buffer layout); splits beyond the current context are simply empty
     const int nsplit = std::min(10, std::min(G / c.num_key_value_heads, (max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS));
     mega::Params p{};
-    p.layers = m.d_dec_layers; p.lm_head = m.lm_head; p.embed = m.embed; p.final_norm = m.final_norm;
+    p.layers = m.d_dec_layers; p.lm_head = m.lm_head; p.embed = m.embed; p.final_norm = m.final_norm_sw;
     p.rope_cos = m.rope_cos; p.rope_sin = m.rope_sin; p.eps = (float)c.rms_norm_eps;
     p.L = c.num_hidden_layers; p.H = c.hidden_size; p.QD = m.d.q_dim; p.KVD = m.d.kv_dim; p.I = c.intermediate_size;
     p.V = c.vocab_size; p.nq = c.num_attention_heads; p.nkv = c.num_key_value_heads; p.group = group;
@@ -828,7 +942,6 @@ void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* 
     p.attn_ll = w; w += m.d.q_dim;
     p.x_ll = w; w += c.hidden_size;
     p.act_ll = w; w += c.intermediate_size;
-    p.cnt = reinterpret_cast<unsigned*>(w);
     p.dbg = mb.dbg;
     g_last_dbg = mb.dbg;
     // tags must stay monotonic for red.max publication: long before the 24-bit epoch wraps, wipe the exchange buffers

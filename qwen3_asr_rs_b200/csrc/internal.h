@@ -71,7 +71,9 @@ struct Model {
     bf16 *embed = nullptr, *lm_head = nullptr;
     std::vector<DecLayerW> dec;
     float* final_norm = nullptr;
-    DecLayerW* d_dec_layers = nullptr;   // device copy of `dec` (pointer table read by the fused decode step)
+    DecLayerW* d_dec_layers = nullptr;   // device copy of `dec` for the fused decode step; its ln_in / ln_post point at
+                                         // copies stored in the step's bank-conflict-free activation layout (decode_mega.cu)
+    float* final_norm_sw = nullptr;      // final norm weight in the same layout
     float *rope_cos = nullptr, *rope_sin = nullptr;   // [rope_max_pos][head_dim/2]
     int rope_max_pos = 0;
 

@@ -131,6 +131,17 @@ template <typename T> static T* dev_alloc(Model* m, size_t n) {
     m->owned.push_back(p);
     return p;
 }
+
+// Copy of an fp32 vector in the activation layout of the fused decode step (decode_mega.cu, xs_swz): 16-byte group k
+// is stored at k ^ ((k >> 3) & 1), which makes the per-lane 32-byte register loads of the GEMV bank-conflict free.
+static float* swizzled_copy(Model* m, const float* dev_src, int n) {
+    std::vector<float> h((size_t)n), o((size_t)n);
+    ASRB_CUDA_CHECK(cudaMemcpy(h.data(), dev_src, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    for (int e = 0; e < n; ++e) { const int k = e >> 2; o[(size_t)((k ^ ((k >> 3) & 1)) << 2) + (e & 3)] = h[e]; }
+    float* d = dev_alloc<float>(m, (size_t)n);
+    ASRB_CUDA_CHECK(cudaMemcpy(d, o.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    return d;
+}
 template <typename T> static T* dev_upload(Model* m, const std::vector<T>& h) {
     T* p = dev_alloc<T>(m, h.size());
     ASRB_CUDA_CHECK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -316,8 +327,13 @@ void model_finalize(Model* m) {
         drop_raw(m, p + ".mlp.gate_proj.weight"); drop_raw(m, p + ".mlp.up_proj.weight");
         w.wdown = take<bf16>(m, p + ".mlp.down_proj.weight", {H, I}, true);
     }
-    m->d_dec_layers = dev_alloc<DecLayerW>(m, m->dec.size());
-    ASRB_CUDA_CHECK(cudaMemcpy(m->d_dec_layers, m->dec.data(), m->dec.size() * sizeof(DecLayerW), cudaMemcpyHostToDevice));
+    {   // pointer table of the fused decode step: norm weights in its swizzled activation layout
+        std::vector<DecLayerW> tab = m->dec;
+        for (DecLayerW& w : tab) { w.ln_in = swizzled_copy(m, w.ln_in, (int)H); w.ln_post = swizzled_copy(m, w.ln_post, (int)H); }
+        m->final_norm_sw = swizzled_copy(m, m->final_norm, (int)H);
+        m->d_dec_layers = dev_alloc<DecLayerW>(m, tab.size());
+        ASRB_CUDA_CHECK(cudaMemcpy(m->d_dec_layers, tab.data(), tab.size() * sizeof(DecLayerW), cudaMemcpyHostToDevice));
+    }
     build_mel_tables(m);
     build_pos_tables(m);
     ASRB_CUDA_CHECK(cudaDeviceSynchronize());

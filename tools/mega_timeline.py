@@ -37,4 +37,9 @@ for cta, row in zip(("cta0", "ctaLast"), t):
     print(cta, "layer-5 detail (cycles): P1 wait", d(1, 0), "gather", d(2, 1), "norm", d(3, 2), "gemv", d(4, 3),
           "| P4 wait", d(9, 8), "gather", d(10, 9), "norm", d(11, 10), "gemv", d(12, 11), "arrive", d(13, 12),
           "| P5 wait", d(17, 16), "gather", d(18, 17), "gemv", d(19, 18), "arrive", d(20, 19))
+for cta, row in zip(("cta0", "ctaLast"), t):
+    f = row[440:464].astype(np.int64)
+    n = int((f != 0).sum())
+    print(cta, "P4 consume warp-0 marks (cycles from entry; entry, xr+sync, then per slot [weights ready, rows done], end):",
+          [int(v - f[0]) for v in f[:n]])
 eng.close()
