@@ -40,7 +40,7 @@ static constexpr int XRES_MAX = 64;
 static constexpr int MAX_LAYERS = 32;                   // layer table staged in shared memory                     // residual rows owned by one CTA (H / gridDim.x, rounded up)
 static constexpr int HD = 128;
 static constexpr int PSTRIDE = HD + 2;                  // partial record: o[128], m, l
-static constexpr int DBG_SLOTS = 512;
+static constexpr int DBG_SLOTS = 1024;
 
 // phases (3 bits of the tag)
 enum { PH_QKV = 1, PH_PART = 2, PH_ATTN = 3, PH_XO = 4, PH_ACT = 5, PH_XD = 6 };
@@ -441,6 +441,14 @@ __device__ __forceinline__ void head_norm_rope(const uint2* __restrict__ src, ui
     do {                                                                                               \
         if (dbg_row && tid == 0 && l == 5) dbg_row[400 + (k)] = clock64();                              \
     } while (0)
+// every CTA: wall-clock (globaltimer, ns) of three events of layer 5 -> row 0, slots [512 + 3 * cta ...)
+#define MEGA_GT(k)                                                                                     \
+    do {                                                                                               \
+        if (p.dbg && tid == 0 && l == 5) {                                                             \
+            unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));               \
+            p.dbg[512 + 3 * blockIdx.x + (k)] = (long long)t_;                                         \
+        }                                                                                              \
+    } while (0)
 #define MEGA_MARK()                                                                                    \
     do {                                                                                               \
         if (dbg_row && tid == 0 && dbg_i < DBG_SLOTS) dbg_row[dbg_i++] = clock64();                    \
@@ -589,60 +597,76 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
         }
         consume<H, ME_STORE>(sl_qkv, ring, q, xs, p.qkv_ll, tl | PH_QKV, xres, best_v, best_i, pb, nr);
         MEGA_FINE(4);
+        MEGA_GT(0);
         MEGA_MARK();
         // ---- phase 2: attention partials, work item = (kv head, 64-key split) ----
         {
-            const int nk = pos + 1;                              // keys 0..pos
-            const int nloc = att_cta ? max(0, min(nk - att_j0, KV_KEYS)) : 0;   // keys of this split incl. the new one
-            const int nact = min(p.nsplit, (pos + KV_KEYS) / KV_KEYS);          // splits holding at least one key
+            // Splits only hold keys that were cached before this step (n_old of them, prefetched by the producer, so a
+            // split depends on nothing but q); the key/value of the current token is folded in as one more partial by the
+            // merging CTA (split 0 of the kv head), which also appends it to the cache.
+            const int nloc = n_old;
+            const int nact = min(p.nsplit, (pos + KV_KEYS - 1) / KV_KEYS);      // splits holding at least one cached key
+            const bool merger = att_cta && att_sp == 0;                         // pos >= 1: split 0 always has cached keys
             if (nloc > 0) {
                 const int g = att_g;
                 float* qs = xs;                       // [group][128]
                 float* kn = qs + p.group * HD;        // [128]
                 float* vn = kn + HD;                  // [128]
                 float* sc = vn + HD;                  // [group][KV_KEYS]
-                float* ml = sc + p.group * KV_KEYS;   // [group][2] (max, sum)
+                float* ml = sc + p.group * KV_KEYS;   // [group][2] (max, sum)   (generic path) / score of the new key per head
                 float* osum = ml + 8;                 // [warps][2][128] per-warp partial outputs (group == 2 path)
+                float* wml = osum + NCONS_WARPS * 2 * HD;   // [warps][2][2] per-warp (max, sum)
+                float* snew = wml + NCONS_WARPS * 4;  // [group] score of the current token's key per head (merging CTA)
                 float* Ks = reinterpret_cast<float*>(kv_smem);
                 float* Vs = reinterpret_cast<float*>(kv_smem + KV_TILE_BYTES);
-                const bool has_new = (pos >= att_j0) && (pos < att_j0 + KV_KEYS);
+                MEGA_FINE(24);
                 cons_sync();                          // xs (phase-1 activations) no longer needed by any warp; q/k/v words are
-                                                      // polled directly below (few readers per word: no counter needed)
+                                                      // polled directly below (few readers per word)
                 if (warp < p.group) head_norm_rope(p.qkv_ll + (size_t)(g * p.group + warp) * HD, tl | PH_QKV, pb + 2 * H, p.eps, cs, sn, qs + warp * HD, lane);
-                else if (warp == p.group && has_new) head_norm_rope(p.qkv_ll + QD + (size_t)g * HD, tl | PH_QKV, pb + 2 * H + HD, p.eps, cs, sn, kn, lane);
-                else if (warp == p.group + 1 && has_new) {
+                else if (warp == p.group && merger) head_norm_rope(p.qkv_ll + QD + (size_t)g * HD, tl | PH_QKV, pb + 2 * H + HD, p.eps, cs, sn, kn, lane);
+                else if (warp == p.group + 1 && merger) {
                     float vv[4];
                     ll_poll4(p.qkv_ll + QD + p.KVD + (size_t)g * HD + lane, 32, tl | PH_QKV, vv);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) vn[lane + 32 * i] = vv[i];
                 }
-                if (n_old > 0) mbar_wait(kv_full, kvq & 1);      // prefetched K/V tiles have landed
+                MEGA_FINE(25);
+                mbar_wait(kv_full, kvq & 1);          // prefetched K/V tiles have landed
                 cons_sync();
-                if (has_new && tid < HD) {            // KV append (replaces Tensor::cat, layers.rs:311-317)
-                    float* kc = p.kcache + (size_t)l * p.cache_layer_stride + ((size_t)g * p.max_ctx + pos) * HD;
-                    float* vc = p.vcache + (size_t)l * p.cache_layer_stride + ((size_t)g * p.max_ctx + pos) * HD;
-                    const float kx = kn[tid], vx = vn[tid];
-                    kc[tid] = kx; vc[tid] = vx;
-                    Ks[(pos - att_j0) * HD + tid] = kx; Vs[(pos - att_j0) * HD + tid] = vx;
+                MEGA_FINE(26);
+                if (merger) {
+                    if (tid < HD) {                   // KV append (replaces Tensor::cat, layers.rs:311-317)
+                        float* kc = p.kcache + (size_t)l * p.cache_layer_stride + ((size_t)g * p.max_ctx + pos) * HD;
+                        float* vc = p.vcache + (size_t)l * p.cache_layer_stride + ((size_t)g * p.max_ctx + pos) * HD;
+                        kc[tid] = kn[tid]; vc[tid] = vn[tid];
+                    }
+                    if (warp >= NCONS_WARPS - p.group) {   // score of the new key for head hq (last `group` warps)
+                        const int hq = warp - (NCONS_WARPS - p.group);
+                        const float4 a = *reinterpret_cast<const float4*>(qs + hq * HD + lane * 4);
+                        const float4 b = *reinterpret_cast<const float4*>(kn + lane * 4);
+                        const float sn_ = warp_sum(fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))));
+                        if (lane == 0) snew[hq] = sn_ / sqrtf((float)HD);
+                    }
                 }
-                cons_sync();
+                MEGA_FINE(27);
                 if (p.group == 2) {
-                    // scores, 2 query heads per kv head: warp w takes keys w, w+8, ...; every lane multiplies its 4 dims of the
-                    // K row (one conflict-free LDS.128) with both q vectors held in registers; the 16 partial sums per lane
-                    // (8 keys x 2 heads) are reduced across the warp with a transposing butterfly (16 shuffles instead of 80)
+                    // 2 query heads per kv head: warp w owns keys w, w+8, ... of the split and computes a complete local softmax
+                    // partial (max, sum, unnormalised output) for them; the 8 warp partials are merged through shared memory
+                    // exactly like the per-split partials are merged later.  One barrier, no score array.
+                    //  scores: every lane multiplies its 4 dims of the K row (one conflict-free LDS.128) with both q vectors held
+                    //  in registers; the 16 partial sums per lane (8 keys x 2 heads) are reduced across the warp with a
+                    //  transposing butterfly (16 shuffles instead of 80); lane 2 * (2 * kk + h) (and its odd twin) ends up
+                    //  with the score of key kk, head h
                     const float4 q0 = *reinterpret_cast<const float4*>(qs + lane * 4);
                     const float4 q1 = *reinterpret_cast<const float4*>(qs + HD + lane * 4);
                     float pv[16];
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {
                         const int j = warp + 8 * kk;
-                        float s0 = 0.f, s1 = 0.f;
-                        if (j < nloc) {
-                            const float4 kv = *reinterpret_cast<const float4*>(Ks + j * HD + lane * 4);
-                            s0 = fmaf(kv.x, q0.x, fmaf(kv.y, q0.y, fmaf(kv.z, q0.z, kv.w * q0.w)));
-                            s1 = fmaf(kv.x, q1.x, fmaf(kv.y, q1.y, fmaf(kv.z, q1.z, kv.w * q1.w)));
-                        }
-                        pv[2 * kk] = s0; pv[2 * kk + 1] = s1;
+                        // branch-free: rows past the split's last key are read (stale data) and masked below
+                        const float4 kv = *reinterpret_cast<const float4*>(Ks + j * HD + lane * 4);
+                        pv[2 * kk] = fmaf(kv.x, q0.x, fmaf(kv.y, q0.y, fmaf(kv.z, q0.z, kv.w * q0.w)));
+                        pv[2 * kk + 1] = fmaf(kv.x, q1.x, fmaf(kv.y, q1.y, fmaf(kv.z, q1.z, kv.w * q1.w)));
                     }
 #pragma unroll
                     for (int o = 16, n = 16; n > 1; o >>= 1, n >>= 1) {
@@ -655,10 +679,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                         }
                     }
                     pv[0] += __shfl_xor_sync(0xffffffffu, pv[0], 1);
-                    {   // lane holds value index (lane >> 1) = kk * 2 + head
-                        const int vi = lane >> 1, j = warp + 8 * (vi >> 1);
-                        if (!(lane & 1) && j < nloc) sc[(vi & 1) * KV_KEYS + j] = pv[0] / sqrtf((float)HD);
+                    const bool mine = warp + 8 * (lane >> 2) < nloc;               // this lane's key exists
+                    const float sv = mine ? pv[0] / sqrtf((float)HD) : -INFINITY;
+                    float mw = sv;                                                   // max over this warp's keys, per head (lane bit 1)
+                    mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, 4));
+                    mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, 8));
+                    mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, 16));
+                    const float ev = mine ? expf(sv - mw) : 0.f;
+                    float lw = ev;
+                    lw += __shfl_xor_sync(0xffffffffu, lw, 4);
+                    lw += __shfl_xor_sync(0xffffffffu, lw, 8);
+                    lw += __shfl_xor_sync(0xffffffffu, lw, 16);
+                    // o_w[h][d] = sum_kk e[kk][h] * V[j][d]: 4 dims per lane (one LDS.128 of V per key), both heads
+                    float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const int j = warp + 8 * kk;
+                        const float4 vv = *reinterpret_cast<const float4*>(Vs + j * HD + lane * 4);
+                        const float e0 = __shfl_sync(0xffffffffu, ev, 4 * kk), e1 = __shfl_sync(0xffffffffu, ev, 4 * kk + 2);
+                        if (j < nloc) {       // (a stale V row may hold non-finite garbage: 0 * inf must not reach the sum)
+                            o0.x = fmaf(e0, vv.x, o0.x); o0.y = fmaf(e0, vv.y, o0.y); o0.z = fmaf(e0, vv.z, o0.z); o0.w = fmaf(e0, vv.w, o0.w);
+                            o1.x = fmaf(e1, vv.x, o1.x); o1.y = fmaf(e1, vv.y, o1.y); o1.z = fmaf(e1, vv.z, o1.z); o1.w = fmaf(e1, vv.w, o1.w);
+                        }
                     }
+                    *reinterpret_cast<float4*>(osum + (warp * 2 + 0) * HD + lane * 4) = o0;
+                    *reinterpret_cast<float4*>(osum + (warp * 2 + 1) * HD + lane * 4) = o1;
+                    if (lane == 0 || lane == 2) { wml[(warp * 2 + (lane >> 1)) * 2] = mw; wml[(warp * 2 + (lane >> 1)) * 2 + 1] = lw; }
+                    cons_sync();
+                    MEGA_FINE(28);
+                    {
+                        const int hq = tid / HD, d = tid - hq * HD;      // NCONS == 2 * HD
+                        float M = -INFINITY;
+#pragma unroll
+                        for (int w8 = 0; w8 < NCONS_WARPS; ++w8) M = fmaxf(M, wml[(w8 * 2 + hq) * 2]);
+                        float acc = 0.f, Ls = 0.f;
+#pragma unroll
+                        for (int w8 = 0; w8 < NCONS_WARPS; ++w8) {
+                            const float f = expf(wml[(w8 * 2 + hq) * 2] - M);           // exp(-inf) = 0: warps without keys
+                            acc = fmaf(f, osum[(w8 * 2 + hq) * HD + d], acc);
+                            Ls = fmaf(f, wml[(w8 * 2 + hq) * 2 + 1], Ls);
+                        }
+                        uint2* rec = p.part_ll + ((size_t)blockIdx.x * 2 + hq) * PSTRIDE;
+                        ll_store(rec + d, acc, tl | PH_PART);
+                        if (d < 2) ll_store(rec + HD + d, d == 0 ? M : Ls, tl | PH_PART);
+                    }
+                    MEGA_FINE(29);
                 } else {
                     // generic group size: one thread per (head, key); the d loop is rotated by the key index so that the
                     // 32 lanes of a warp hit 32 different banks of the row-major K tile
@@ -675,49 +740,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                             sc[hq * KV_KEYS + j] = (a0 + a1) / sqrtf((float)HD);
                         }
                     }
-                }
-                cons_sync();
-                if (warp < p.group) {                 // softmax partial of head `warp` over this split
-                    float mx = -INFINITY;
-                    for (int j = lane; j < nloc; j += 32) mx = fmaxf(mx, sc[warp * KV_KEYS + j]);
-                    mx = warp_max(mx);
-                    float sum = 0.f;
-                    for (int j = lane; j < nloc; j += 32) {
-                        float e = expf(sc[warp * KV_KEYS + j] - mx);
-                        sc[warp * KV_KEYS + j] = e; sum += e;
-                    }
-                    sum = warp_sum(sum);
-                    if (lane == 0) { ml[warp * 2] = mx; ml[warp * 2 + 1] = sum; }
-                }
-                cons_sync();
-                // o[hq][d] = sum_j e[hq][j] * V[j][d]; publish the partial record
-                if (p.group == 2) {
-                    // warp w accumulates keys w, w+8, ... for 4 dims per lane (one LDS.128 of V per key) and both heads;
-                    // the 8 per-warp partial vectors are then summed through shared memory by thread = (head, d)
-                    float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                        const int j = warp + 8 * kk;
-                        if (j < nloc) {
-                            const float4 vv = *reinterpret_cast<const float4*>(Vs + j * HD + lane * 4);
-                            const float e0 = sc[j], e1 = sc[KV_KEYS + j];
-                            o0.x = fmaf(e0, vv.x, o0.x); o0.y = fmaf(e0, vv.y, o0.y); o0.z = fmaf(e0, vv.z, o0.z); o0.w = fmaf(e0, vv.w, o0.w);
-                            o1.x = fmaf(e1, vv.x, o1.x); o1.y = fmaf(e1, vv.y, o1.y); o1.z = fmaf(e1, vv.z, o1.z); o1.w = fmaf(e1, vv.w, o1.w);
-                        }
-                    }
-                    *reinterpret_cast<float4*>(osum + (warp * 2 + 0) * HD + lane * 4) = o0;
-                    *reinterpret_cast<float4*>(osum + (warp * 2 + 1) * HD + lane * 4) = o1;
                     cons_sync();
-                    {
-                        const int hq = tid / HD, d = tid - hq * HD;      // NCONS == 2 * HD
-                        float acc = 0.f;
-#pragma unroll
-                        for (int w8 = 0; w8 < NCONS_WARPS; ++w8) acc += osum[(w8 * 2 + hq) * HD + d];
-                        uint2* rec = p.part_ll + ((size_t)blockIdx.x * 2 + hq) * PSTRIDE;
-                        ll_store(rec + d, acc, tl | PH_PART);
-                        if (d < 2) ll_store(rec + HD + d, ml[hq * 2 + d], tl | PH_PART);
+                    if (warp < p.group) {                 // softmax partial of head `warp` over this split
+                        float mx = -INFINITY;
+                        for (int j = lane; j < nloc; j += 32) mx = fmaxf(mx, sc[warp * KV_KEYS + j]);
+                        mx = warp_max(mx);
+                        float sum = 0.f;
+                        for (int j = lane; j < nloc; j += 32) {
+                            float e = expf(sc[warp * KV_KEYS + j] - mx);
+                            sc[warp * KV_KEYS + j] = e; sum += e;
+                        }
+                        sum = warp_sum(sum);
+                        if (lane == 0) { ml[warp * 2] = mx; ml[warp * 2 + 1] = sum; }
                     }
-                } else {
+                    cons_sync();
                     for (int idx = tid; idx < p.group * HD; idx += NCONS) {
                         const int hq = idx / HD, d = idx - hq * HD;
                         float acc = 0.f;
@@ -727,16 +763,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                         if (d < 2) ll_store(rec + HD + d, ml[hq * 2 + d], tl | PH_PART);
                     }
                 }
-                if (n_old > 0) {                      // hand the K/V staging buffer back to the producer
+                {                                     // hand the K/V staging buffer back to the producer
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(kv_empty);
                     ++kvq;
                 }
+                MEGA_FINE(30);
+                MEGA_GT(1);
                 // split 0 of every kv head merges the partials of all active splits and publishes the head outputs
-                if (att_sp == 0) {
+                if (merger) {
                     for (int idx = tid; idx < p.group * HD; idx += NCONS) {
-                        const int hq = idx / HD, d = idx - hq * HD;
+                        const int hq = idx / HD, d = idx - hq * HD;          // hq is uniform per warp (HD = 4 warps)
                         // lane s of every warp fetches (max, sum) of split s; every thread fetches o[s][d] of all active
                         // splits; all loads are issued before any tag is examined (one round trip when ready)
                         constexpr int SB = 10;                       // nsplit <= 10 enforced by decode_mega_supported
@@ -763,29 +801,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                             for (int u = 0; u < SB; ++u) if (u < nact) ok = ok && (ov[u].y == tg);
                             ok = __all_sync(0xffffffffu, ok);
                         } while (!ok);
-                        float M = -INFINITY, Lsum = 0.f, O = 0.f;
+                        MEGA_FINE(35);
+                        // softmax merge, one partial per lane: lanes < nact hold a split, lane nact the current token's key
+                        // (max = its score, sum = 1, output = its value row)
+                        const float m_l = lane < nact ? __uint_as_float(mv.x) : (lane == nact ? snew[hq] : -INFINITY);
+                        const float l_l = lane < nact ? __uint_as_float(lv.x) : (lane == nact ? 1.f : 0.f);
+                        const float M = warp_max(m_l);
+                        const float f = expf(m_l - M);                       // exp(-inf) = 0 on idle lanes
+                        const float Lsum = warp_sum(f * l_l);
+                        float O = __shfl_sync(0xffffffffu, f, nact) * vn[d];
 #pragma unroll
-                        for (int u = 0; u < SB; ++u) {
-                            if (u < nact) {
-                                const float ms = __uint_as_float(__shfl_sync(0xffffffffu, mv.x, u));
-                                const float ls = __uint_as_float(__shfl_sync(0xffffffffu, lv.x, u));
-                                const float os = __uint_as_float(ov[u].x);
-                                const float Mn = fmaxf(M, ms);
-                                const float a = expf(M - Mn), b = expf(ms - Mn);     // exp(-inf) = 0 on the first split
-                                Lsum = Lsum * a + ls * b; O = O * a + os * b; M = Mn;
-                            }
-                        }
+                        for (int u = 0; u < SB; ++u)
+                            if (u < nact) O = fmaf(__shfl_sync(0xffffffffu, f, u), __uint_as_float(ov[u].x), O);
                         ll_store(p.attn_ll + (size_t)(g * p.group + hq) * HD + d, O / Lsum, tl | PH_ATTN);
                     }
                 }
+                MEGA_FINE(31);
                 cons_sync();                          // attention scratch (aliases xs) is free again
             }
         }
         MEGA_MARK();
         // ---- phase 3: o_proj GEMV + residual ----
+        MEGA_FINE(32);
         ll_gather(p.attn_ll, QD, tl | PH_ATTN, xs);
+        MEGA_FINE(33);
+        MEGA_GT(2);
         cons_sync();
         consume<QD, ME_RESID>(sl_o, ring, q, xs, p.x_ll, tl | PH_XO, xres, best_v, best_i);
+        MEGA_FINE(34);
         MEGA_MARK();
         // ---- phase 4: RMSNorm + gate/up GEMV + SiLU*mul ----
         cons_sync();
@@ -897,7 +940,7 @@ bool decode_mega_supported(const Model& m, int B, int ctx) {
     if (B != 1 || c.head_dim != 128) return false;
     const int group = c.num_attention_heads / c.num_key_value_heads;
     if (group + 2 > mega::NCONS_WARPS) return false;
-    if ((size_t)(group * 128 + 256 + group * mega::KV_KEYS + 8 + mega::NCONS_WARPS * 2 * 128) > (size_t)mega::XS_FLOATS) return false;
+    if ((size_t)(group * 128 + 256 + group * mega::KV_KEYS + 8 + mega::NCONS_WARPS * 2 * 128 + mega::NCONS_WARPS * 4 + 8) > (size_t)mega::XS_FLOATS) return false;
     if (m.ctx->smem_optin < mega_smem_bytes()) return false;
     if ((c.hidden_size + m.ctx->sm_count - 1) / m.ctx->sm_count + 1 > mega::XRES_MAX) return false;
     if (c.num_hidden_layers > 32) return false;                  // 5-bit layer field

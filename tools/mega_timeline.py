@@ -16,8 +16,8 @@ for _ in range(2):
     r = eng.transcribe_ids([x], max_new_tokens=32)
 print("stage_ms", r.stage_ms, "us/step", 1e3 * r.stage_ms["decode"] / max(r.decode_steps, 1))
 lib = _lib.load_library()
-buf = (C.c_longlong * 1024)()
-n = lib.asrb_debug_mega_timeline(buf, 1024)
+buf = (C.c_longlong * 2048)()
+n = lib.asrb_debug_mega_timeline(buf, 2048)
 t = np.array(buf[:], dtype=np.int64).reshape(2, -1)
 L = cfg.text.num_hidden_layers
 names = ["p1_qkv", "p2_attn", "p3_oproj", "p4_gateup", "p5_down"]   # each includes the wait for its inputs
@@ -38,8 +38,19 @@ for cta, row in zip(("cta0", "ctaLast"), t):
           "| P4 wait", d(9, 8), "gather", d(10, 9), "norm", d(11, 10), "gemv", d(12, 11), "arrive", d(13, 12),
           "| P5 wait", d(17, 16), "gather", d(18, 17), "gemv", d(19, 18), "arrive", d(20, 19))
 for cta, row in zip(("cta0", "ctaLast"), t):
+    f = row[400:440].astype(np.int64)
+    if f[24]:
+        names2 = ["sync+poll qkv", "kv tile+sync", "append+sync", "warp partials+sync", "combine+publish", "release"]
+        print(cta, "layer-5 P2/P3 detail (cycles):", ", ".join(f"{nm} {int(f[25 + i] - f[24 + i])}" for i, nm in enumerate(names2)),
+              "| merge: poll", int(f[35] - f[30]), "math+publish", int(f[31] - f[35]), "| P3: gather", int(f[33] - f[32]), "o_proj", int(f[34] - f[33]))
+for cta, row in zip(("cta0", "ctaLast"), t):
     f = row[440:464].astype(np.int64)
     n = int((f != 0).sum())
     print(cta, "P4 consume warp-0 marks (cycles from entry; entry, xr+sync, then per slot [weights ready, rows done], end):",
           [int(v - f[0]) for v in f[:n]])
+g = t[0][512:512 + 3 * 148].reshape(148, 3).astype(np.int64)
+t0 = g[:, 0].min()
+print("layer-5 wall clock per CTA (ns after the first CTA left P1): [P1 done, partial published, P3 gather done]")
+for c in list(range(0, 72)) + [100, 147]:
+    print(f"  cta {c:3d}: {int(g[c,0]-t0):6d} {int(g[c,1]-t0) if g[c,1] else -1:6d} {int(g[c,2]-t0):6d}")
 eng.close()
