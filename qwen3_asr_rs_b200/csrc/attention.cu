@@ -115,12 +115,15 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_kernel(AttnParams p) {
     }
 }
 
-bool launch_attention_tc(const AttnParams& p, int hd, cudaStream_t st);   // attention_tc.cu
+bool launch_attention_tc(const AttnParams& p, int hd, cudaStream_t st);    // attention_tc.cu  (3xTF32 mma.sync; ASRB_ATTN=tc)
+bool launch_attention_f32(const AttnParams& p, int hd, cudaStream_t st);   // attention_f32.cu (register-tiled fp32; default)
 
 void launch_attention(const AttnParams& p, int hd, cudaStream_t st) {
     if (p.nseg <= 0 || p.max_len <= 0) return;
-    static const bool force_simt = [] { const char* e = getenv("ASRB_ATTN"); return e && std::string(e) == "simt"; }();
-    if (!force_simt && launch_attention_tc(p, hd, st)) return;
+    // 0 = register-tiled fp32 (default), 1 = 3xTF32 tensor-core variant, 2 = the simple kernel below
+    static const int which = [] { const char* e = getenv("ASRB_ATTN"); return !e ? 0 : std::string(e) == "tc" ? 1 : std::string(e) == "simt" ? 2 : 0; }();
+    if (which == 0 && launch_attention_f32(p, hd, st)) return;
+    if (which == 1 && launch_attention_tc(p, hd, st)) return;
     dim3 grid((p.max_len + QT - 1) / QT, p.nheads, p.nseg);
     if (hd == 64) {
         size_t smem = (QT * 65 + KT * 65 + KT * 64 + QT * KT) * sizeof(float);
