@@ -32,8 +32,7 @@ __global__ void __launch_bounds__(THREADS, 2) attn_f32_kernel(AttnParams p) {
     float* Ps = Vs + KT * HD;                   // [QT][PS]
     const int seg = blockIdx.z, h = blockIdx.y;
     const int q0 = p.seg_q0[seg], len = p.seg_len[seg];
-    const int qt0 = blockIdx.x * QT;
-    if (qt0 >= len) return;
+    const int nqt = (len + QT - 1) / QT;
     const int gkv = h / p.group;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const float* kbase; const float* vbase;
@@ -44,6 +43,16 @@ __global__ void __launch_bounds__(THREADS, 2) attn_f32_kernel(AttnParams p) {
         kbase = p.k + (size_t)seg * p.seg_stride + (size_t)gkv * p.head_stride;
         vbase = p.v + (size_t)seg * p.seg_stride + (size_t)gkv * p.head_stride;
     }
+    // Causal segments: a query tile needs keys up to its own end only, so tile x costs ~(x + 1) key tiles.  One CTA takes
+    // tiles x and nqt-1-x back to back: every CTA then has the same amount of work (the long tiles alone made the kernel
+    // twice as long as its average SM was busy).  Non-causal segments: one tile per CTA.
+    const int npass = p.causal ? 2 : 1;
+    for (int pass = 0; pass < npass; ++pass) {
+    const int qtile = pass == 0 ? (int)blockIdx.x : nqt - 1 - (int)blockIdx.x;
+    // causal: CTA x owns tiles x (x < ceil(nqt / 2)) and nqt-1-x (when that is a different, later tile)
+    if (qtile >= nqt || qtile < 0 || (p.causal && pass == 0 && 2 * qtile >= nqt) || (pass == 1 && qtile <= (int)blockIdx.x)) continue;
+    const int qt0 = qtile * QT;
+    __syncthreads();                            // previous pass done with Qt / Ps
     // Q tile, transposed on the way in (lanes run along the rows: conflict-free scalar stores); rows >= len are zero
     {
         constexpr int NQ = QT * (HD / 4) / THREADS;          // 8 (head_dim 128) or 4 (64): one batch
@@ -185,6 +194,7 @@ __global__ void __launch_bounds__(THREADS, 2) attn_f32_kernel(AttnParams p) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) store_split3(p.out_s3, p.plane_stride, base + gq * 64 + tx * 4 + e, o[i][gq][e] * inv);
     }
+    }   // pass
 }
 
 template <int HD> static size_t smem_bytes() { return (size_t)(HD * QT + HD * KT + KT * HD + QT * PS) * sizeof(float); }
@@ -195,7 +205,8 @@ bool launch_attention_f32(const AttnParams& p, int hd, cudaStream_t st) {
     using namespace af32;
     if (p.nseg <= 0 || p.max_len <= 0) return true;
     if ((p.ldq % 4) || (p.ldk % 4) || (p.head_stride % 4) || (p.seg_stride % 4)) return false;
-    dim3 grid((p.max_len + QT - 1) / QT, p.nheads, p.nseg);
+    const int nqt_max = (p.max_len + QT - 1) / QT;
+    dim3 grid(p.causal ? (nqt_max + 1) / 2 : nqt_max, p.nheads, p.nseg);
     if (hd == 64) {
         static bool attr = false;
         if (!attr) { ASRB_CUDA_CHECK(cudaFuncSetAttribute(attn_f32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<64>())); attr = true; }
