@@ -193,6 +193,33 @@ def test_full_size_0p6b_one_clip(report):
         eng.close()
 
 
+def test_full_size_1p7b_short_clip(report):
+    """Qwen3-ASR-1.7B dims (BASELINE.json configs[3] model; dims as recalled in SURVEY.md section 8), one 10 s clip,
+    synthetic weights: exact ids + logits tolerance.  These dims are outside the fused decode step's table, so this
+    also covers the per-phase decode path at full size."""
+    from qwen3_asr_rs_b200 import AsrInference, config_1p7b
+    cfg = O.cfg_1p7b()
+    w = synth.make_weights(cfg, 3)
+    x = synth.make_clip(7, 10.0)
+    n_new = 6
+    ref = O.transcribe_ids(O.OracleModel(cfg, w), x, max_new_tokens=n_new, keep_logits=True, lm_head_all_rows=False)
+    eng = AsrInference.from_weights(config_1p7b(), w, device=0)
+    try:
+        eng.mel([x])
+        enc = eng.encode()[0]
+        report["full1p7b_enc_rel_err"] = _rel(enc, ref.audio_embeds.numpy())
+        seq, logits = eng.prefill()
+        report["full1p7b_prefill_logits_rel_err"] = _rel(logits[0], ref.prefill_logits.numpy())
+        assert enc.shape == (130, 2048) and seq[0] == 145
+        got = eng.transcribe_ids([x], max_new_tokens=n_new)
+        report["full1p7b_stage_ms"] = got.stage_ms
+        assert report["full1p7b_enc_rel_err"] <= ENC_RTOL
+        assert report["full1p7b_prefill_logits_rel_err"] <= LOGIT_RTOL
+        assert got.ids[0] == ref.ids
+    finally:
+        eng.close()
+
+
 @pytest.mark.parametrize("shards", [1, 3])
 def test_model_load_from_directory(tiny, tmp_path, shards):
     """AsrInference::load (inference.rs:30-86): config.json + model.safetensors / sharded index
