@@ -33,10 +33,10 @@ static constexpr int NCONS_WARPS = 8;
 static constexpr int NCONS = NCONS_WARPS * 32;          // 256 consumer threads
 static constexpr int NTHREADS = NCONS + 32;             // + 1 producer warp
 static constexpr int SLOT_BYTES = 32 * 1024;           // 16 rows of K = 1024: one row per half-warp and pass
-static constexpr int NSLOT = 4;                         // weight ring: 128 KB in flight per SM
+static constexpr int NSLOT_MAX = 4;                     // weight ring: 4 x 32 KB in flight per SM (3 for the 1.7B dims: larger vectors)
 static constexpr int KV_KEYS = 64;                      // keys per attention split (K and V tiles staged in smem)
 static constexpr int KV_TILE_BYTES = KV_KEYS * 128 * 4; // 32 KB each for K and V (fp32 cache)
-static constexpr int XS_FLOATS = 3072 + 64;             // activation vector / attention scratch
+static constexpr int XS_MIN = 3072;                     // activation vector / attention scratch: max(I, XS_MIN) + 64 floats
 static constexpr int XRES_MAX = 64;
 static constexpr int MAX_LAYERS = 32;                   // layer table staged in shared memory                     // residual rows owned by one CTA (H / gridDim.x, rounded up)
 static constexpr int HD = 128;
@@ -169,6 +169,7 @@ __device__ __forceinline__ float ll_gather(const uint2* buf, int n, uint32_t tag
 
 struct Ring {
     uint8_t* slots; uint64_t* full; uint64_t* empty;
+    uint32_t nslot;         // ring depth (compile-time constant of the instantiation, propagated through inlining)
 };
 
 // one weight phase as seen by a CTA: rows [r0, r1) of W[N][K]
@@ -226,7 +227,7 @@ template <class Cursor>
 __device__ __forceinline__ void produce(const Slice& s, const Ring& ring, uint32_t& q, Cursor& pf, const Params& p) {
     for (int r = s.r0; r < s.r1; r += s.rpc, ++q) {
         int rows = min(s.rpc, s.r1 - r);
-        uint32_t slot = q % NSLOT, par = (q / NSLOT) & 1;
+        uint32_t slot = q % ring.nslot, par = (q / ring.nslot) & 1;
         mbar_wait(&ring.empty[slot], par ^ 1);
         uint32_t bytes = (uint32_t)rows * s.K * 2;
         mbar_expect_tx(&ring.full[slot], bytes);
@@ -348,7 +349,7 @@ __device__ __forceinline__ void consume(const Slice& s, const Ring& ring, uint32
     int unit = 0;                                  // unit index within this CTA's slice (kept a multiple of UPW per slot)
     for (int r = s.r0; r < s.r1; r += s.rpc, ++q) {
         const int rows = min(s.rpc, s.r1 - r);
-        const uint32_t slot = q % NSLOT, par = (q / NSLOT) & 1;
+        const uint32_t slot = q % ring.nslot, par = (q / ring.nslot) & 1;
         mbar_wait(&ring.full[slot], par);
         CF();
         const uint4* base = reinterpret_cast<const uint4*>(ring.slots + (size_t)slot * SLOT_BYTES);
@@ -455,23 +456,25 @@ __device__ __forceinline__ void head_norm_rope(const uint2* __restrict__ src, ui
         if (dbg_row && tid == 0 && dbg_i < DBG_SLOTS) dbg_row[dbg_i++] = clock64();                    \
     } while (0)
 
-template <int H, int QD, int I>
+template <int H, int QD, int I, int NS>
 __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p) {
+    constexpr int XS_FLOATS = (I > XS_MIN ? I : XS_MIN) + 64;
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int PARAM_FLOATS = 2 * H + 2 * HD;      // per-layer small vectors: ln_in[H], ln_post[H], q_norm[128], k_norm[128]
     Ring ring;
     ring.slots = smem;
-    uint8_t* kv_smem = smem + (size_t)NSLOT * SLOT_BYTES;              // [K tile | V tile]
+    ring.nslot = NS;
+    uint8_t* kv_smem = smem + (size_t)NS * SLOT_BYTES;              // [K tile | V tile]
     float* xs = reinterpret_cast<float*>(kv_smem + 2 * KV_TILE_BYTES);
     float* xres = xs + XS_FLOATS;                                      // [XRES_MAX] residual rows owned by this CTA
     float* pbuf = xres + XRES_MAX;                                     // [2][PARAM_FLOATS] per-layer small vectors (double buffer)
     float* ropes = pbuf + 2 * PARAM_FLOATS;                            // [128] cos | sin of this step's position
     DecLayerW* ltab = reinterpret_cast<DecLayerW*>(ropes + 128);       // [MAX_LAYERS]
     uint64_t* bars = reinterpret_cast<uint64_t*>(ltab + MAX_LAYERS);
-    ring.full = bars; ring.empty = bars + NSLOT;
-    uint64_t* kv_full = bars + 2 * NSLOT; uint64_t* kv_empty = kv_full + 1;
+    ring.full = bars; ring.empty = bars + NSLOT_MAX;
+    uint64_t* kv_full = bars + 2 * NSLOT_MAX; uint64_t* kv_empty = kv_full + 1;
     uint64_t* p_full = kv_empty + 1; uint64_t* p_empty = p_full + 2;   // [2] each
-    float* red = reinterpret_cast<float*>(bars + 2 * NSLOT + 6);      // [64]
+    float* red = reinterpret_cast<float*>(bars + 2 * NSLOT_MAX + 6);      // [64]
     int* ired = reinterpret_cast<int*>(red + 64);                      // [64]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_producer = warp == NCONS_WARPS;
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     if (__ldcg(p.done) != 0) return;            // sequence finished: nothing to do this step
 
     if (tid == 0) {
-        for (int i = 0; i < NSLOT; ++i) { mbar_init(&ring.full[i], 1); mbar_init(&ring.empty[i], NCONS_WARPS); }
+        for (int i = 0; i < NS; ++i) { mbar_init(&ring.full[i], 1); mbar_init(&ring.empty[i], NCONS_WARPS); }
         mbar_init(kv_full, 1); mbar_init(kv_empty, NCONS_WARPS);
         for (int i = 0; i < 2; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], NCONS_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -924,11 +927,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
 // host side ---------------------------------------------------------------------------------------
 static long long* g_last_dbg = nullptr;   // debug only (ASRB_MEGA_DEBUG): timeline buffer of the last launch
 
-static size_t mega_smem_bytes(int H = 1024) {
-    return (size_t)mega::NSLOT * mega::SLOT_BYTES + 2 * mega::KV_TILE_BYTES +
-           (mega::XS_FLOATS + mega::XRES_MAX + 2 * (2 * H + 2 * mega::HD) + 128) * 4 + mega::MAX_LAYERS * sizeof(DecLayerW) +
-           (2 * mega::NSLOT + 6) * 8 + 64 * 4 + 64 * 4 + 64;
+static int mega_xs_floats(int I) { return std::max(I, mega::XS_MIN) + 64; }
+static size_t mega_smem_bytes(int H, int I, int nslot) {
+    return (size_t)nslot * mega::SLOT_BYTES + 2 * mega::KV_TILE_BYTES +
+           (mega_xs_floats(I) + mega::XRES_MAX + 2 * (2 * H + 2 * mega::HD) + 128) * 4 + mega::MAX_LAYERS * sizeof(DecLayerW) +
+           (2 * mega::NSLOT_MAX + 6) * 8 + 64 * 4 + 64 * 4 + 64;
 }
+// instantiations: (hidden, q_dim, intermediate) -> ring depth
+static int mega_nslot(const asrb_dims& c) { return c.hidden_size > 1024 ? 3 : 4; }
 
 template <int H, int QD, int I> static bool dims_match(const asrb_dims& c) {
     return c.hidden_size == H && c.num_attention_heads * c.head_dim == QD && c.intermediate_size == I;
@@ -941,13 +947,13 @@ bool decode_mega_supported(const Model& m, int B, int ctx) {
     if (B < 1 || c.head_dim != 128) return false;      // batch > 1: one fused launch per sequence, back to back
     const int group = c.num_attention_heads / c.num_key_value_heads;
     if (group + 2 > mega::NCONS_WARPS) return false;
-    if ((size_t)(group * 128 + 256 + group * mega::KV_KEYS + 8 + mega::NCONS_WARPS * 2 * 128 + mega::NCONS_WARPS * 4 + 8) > (size_t)mega::XS_FLOATS) return false;
-    if (m.ctx->smem_optin < mega_smem_bytes()) return false;
+    if ((size_t)(group * 128 + 256 + group * mega::KV_KEYS + 8 + mega::NCONS_WARPS * 2 * 128 + mega::NCONS_WARPS * 4 + 8) > (size_t)mega_xs_floats(c.intermediate_size)) return false;
+    if (m.ctx->smem_optin < mega_smem_bytes(c.hidden_size, c.intermediate_size, mega_nslot(c))) return false;
     if ((c.hidden_size + m.ctx->sm_count - 1) / m.ctx->sm_count + 1 > mega::XRES_MAX) return false;
     if (c.num_hidden_layers > 32) return false;                  // 5-bit layer field
     if ((max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS > 10) return false;                           // merge loop bound (SB)
     if (((max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS) * c.num_key_value_heads > m.ctx->sm_count) return false;   // one CTA per (kv head, 64-key split)
-    return dims_match<1024, 2048, 3072>(c) || dims_match<256, 512, 512>(c);
+    return dims_match<1024, 2048, 3072>(c) || dims_match<2048, 2048, 6144>(c) || dims_match<256, 512, 512>(c);
 }
 
 // floats of session scratch the fused step needs: tagged exchange buffers (2 floats per value)
@@ -969,10 +975,11 @@ void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* 
     const int group = c.num_attention_heads / c.num_key_value_heads;
     // split count is fixed per session (buffer layout); splits beyond the current context are simply empty
     const int nsplit = std::min(10, std::min(G / c.num_key_value_heads, (max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS));
-    const size_t smem = mega_smem_bytes(c.hidden_size);
+    const size_t smem = mega_smem_bytes(c.hidden_size, c.intermediate_size, mega_nslot(c));
     const void* fn = nullptr;
-    if (dims_match<1024, 2048, 3072>(c)) fn = (const void*)mega::decode_step_kernel<1024, 2048, 3072>;
-    else fn = (const void*)mega::decode_step_kernel<256, 512, 512>;
+    if (dims_match<1024, 2048, 3072>(c)) fn = (const void*)mega::decode_step_kernel<1024, 2048, 3072, 4>;          // Qwen3-ASR-0.6B
+    else if (dims_match<2048, 2048, 6144>(c)) fn = (const void*)mega::decode_step_kernel<2048, 2048, 6144, 3>;     // Qwen3-ASR-1.7B
+    else fn = (const void*)mega::decode_step_kernel<256, 512, 512, 4>;                                             // test config
     ASRB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // The kernel handles one sequence.  A batch runs as B launches on the stream (weights are re-streamed per sequence:
     // 2.0 k tokens/s at any batch size, still ~1.8x the per-phase path at batch 8); a sequence that has finished
