@@ -22,7 +22,7 @@
 //   * the last CTA to finish the lm_head performs the greedy bookkeeping (argmax, EOS, append,
 //     embedding of the next token), so there is no host sync and no extra launch per token.
 // Reference semantics per phase: see decode.cu.  The kernel advances ONE sequence; a batch is B back-to-back launches
-// (decode.cu remains the path for logits output, other model dimensions and contexts beyond 640 keys).
+// (decode.cu remains the path for logits output, other model dimensions and contexts beyond 1152 keys).
 #include "internal.h"
 
 namespace asrb {
@@ -42,6 +42,7 @@ static constexpr int MAX_LAYERS = 32;                   // layer table staged in
 static constexpr int HD = 128;
 static constexpr int PSTRIDE = HD + 2;                  // partial record: o[128], m, l
 static constexpr int DBG_SLOTS = 1024;
+static constexpr int MAX_SPLITS = 18;                   // 64-key attention splits per kv head: contexts up to 1152 keys (148 SMs / 8 kv heads = 18)
 
 // phases (3 bits of the tag)
 enum { PH_QKV = 1, PH_PART = 2, PH_ATTN = 3, PH_XO = 4, PH_ACT = 5, PH_XD = 6 };
@@ -779,31 +780,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                 if (merger) {
                     for (int idx = tid; idx < p.group * HD; idx += NCONS) {
                         const int hq = idx / HD, d = idx - hq * HD;          // hq is uniform per warp (HD = 4 warps)
-                        // lane s of every warp fetches (max, sum) of split s; every thread fetches o[s][d] of all active
-                        // splits; all loads are issued before any tag is examined (one round trip when ready)
-                        constexpr int SB = 10;                       // nsplit <= 10 enforced by decode_mega_supported
+                        // lane s of every warp fetches (max, sum) of split s (nact <= MAX_SPLITS <= 32 lanes); all loads of a
+                        // round are issued before any tag is examined (one round trip when ready)
                         const uint32_t tg = tl | PH_PART;
-                        uint2 ov[SB], mv, lv;
+                        constexpr int RB = 9;                                // partial outputs fetched per round (registers)
+                        uint2 mv, lv, ov[RB];
                         bool ok;
-                        do {
-                            ok = true;
+                        auto load_round = [&](int u0) {
+#pragma unroll
+                            for (int u = 0; u < RB; ++u) {
+                                if (u0 + u < nact) {
+                                    const uint2* rec = p.part_ll + ((size_t)(g * p.nsplit + u0 + u) * p.group + hq) * PSTRIDE;
+                                    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(ov[u].x), "=r"(ov[u].y) : "l"(rec + d) : "memory");
+                                }
+                            }
+                        };
+                        auto round_ok = [&](int u0) {
+                            bool k = true;
+#pragma unroll
+                            for (int u = 0; u < RB; ++u) if (u0 + u < nact) k = k && (ov[u].y == tg);
+                            return k;
+                        };
+                        do {        // first round: (max, sum) of every split + the first RB partial outputs, one round trip
                             mv.y = tg; lv.y = tg; mv.x = 0u; lv.x = 0u;
                             if (lane < nact) {
                                 const uint2* rec = p.part_ll + ((size_t)(g * p.nsplit + lane) * p.group + hq) * PSTRIDE;
                                 asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(mv.x), "=r"(mv.y) : "l"(rec + HD) : "memory");
                                 asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(lv.x), "=r"(lv.y) : "l"(rec + HD + 1) : "memory");
                             }
-#pragma unroll
-                            for (int u = 0; u < SB; ++u) {
-                                if (u < nact) {
-                                    const uint2* rec = p.part_ll + ((size_t)(g * p.nsplit + u) * p.group + hq) * PSTRIDE;
-                                    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(ov[u].x), "=r"(ov[u].y) : "l"(rec + d) : "memory");
-                                }
-                            }
-                            ok = (mv.y == tg) && (lv.y == tg);
-#pragma unroll
-                            for (int u = 0; u < SB; ++u) if (u < nact) ok = ok && (ov[u].y == tg);
-                            ok = __all_sync(0xffffffffu, ok);
+                            load_round(0);
+                            ok = __all_sync(0xffffffffu, (mv.y == tg) && (lv.y == tg) && round_ok(0));
                         } while (!ok);
                         MEGA_FINE(35);
                         // softmax merge, one partial per lane: lanes < nact hold a split, lane nact the current token's key
@@ -814,9 +820,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                         const float f = expf(m_l - M);                       // exp(-inf) = 0 on idle lanes
                         const float Lsum = warp_sum(f * l_l);
                         float O = __shfl_sync(0xffffffffu, f, nact) * vn[d];
+                        for (int u0 = 0; u0 < nact; u0 += RB) {              // contexts beyond 9 splits: one more round trip each
+                            if (u0 > 0) { do { load_round(u0); ok = __all_sync(0xffffffffu, round_ok(u0)); } while (!ok); }
 #pragma unroll
-                        for (int u = 0; u < SB; ++u)
-                            if (u < nact) O = fmaf(__shfl_sync(0xffffffffu, f, u), __uint_as_float(ov[u].x), O);
+                            for (int u = 0; u < RB; ++u)
+                                if (u0 + u < nact) O = fmaf(__shfl_sync(0xffffffffu, f, u0 + u), __uint_as_float(ov[u].x), O);
+                        }
                         ll_store(p.attn_ll + (size_t)(g * p.group + hq) * HD + d, O / Lsum, tl | PH_ATTN);
                     }
                 }
@@ -951,7 +960,7 @@ bool decode_mega_supported(const Model& m, int B, int ctx) {
     if (m.ctx->smem_optin < mega_smem_bytes(c.hidden_size, c.intermediate_size, mega_nslot(c))) return false;
     if ((c.hidden_size + m.ctx->sm_count - 1) / m.ctx->sm_count + 1 > mega::XRES_MAX) return false;
     if (c.num_hidden_layers > 32) return false;                  // 5-bit layer field
-    if ((max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS > 10) return false;                           // merge loop bound (SB)
+    if ((max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS > mega::MAX_SPLITS) return false;                           // merge loop bound (SB)
     if (((max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS) * c.num_key_value_heads > m.ctx->sm_count) return false;   // one CTA per (kv head, 64-key split)
     return dims_match<1024, 2048, 3072>(c) || dims_match<2048, 2048, 6144>(c) || dims_match<256, 512, 512>(c);
 }
@@ -974,7 +983,7 @@ void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* 
     const int G = m.ctx->sm_count;
     const int group = c.num_attention_heads / c.num_key_value_heads;
     // split count is fixed per session (buffer layout); splits beyond the current context are simply empty
-    const int nsplit = std::min(10, std::min(G / c.num_key_value_heads, (max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS));
+    const int nsplit = std::min(mega::MAX_SPLITS, std::min(G / c.num_key_value_heads, (max_ctx + mega::KV_KEYS - 1) / mega::KV_KEYS));
     const size_t smem = mega_smem_bytes(c.hidden_size, c.intermediate_size, mega_nslot(c));
     const void* fn = nullptr;
     if (dims_match<1024, 2048, 3072>(c)) fn = (const void*)mega::decode_step_kernel<1024, 2048, 3072, 4>;          // Qwen3-ASR-0.6B

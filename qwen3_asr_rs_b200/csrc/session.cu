@@ -494,7 +494,7 @@ void session_generate(Session* s, int max_new_tokens, int32_t* ids_out, int32_t*
     const int check_every = 16;
     bool all_done = false;
     for (int it = 0; it < steps && !all_done; ++it) {
-        // the fused step covers contexts up to 640 keys; beyond that (long generations) the per-phase path takes over
+        // the fused step covers contexts up to 1152 keys; beyond that (long generations) the per-phase path takes over
         if (use_mega(s, false)) forward_step(s, false);
         else { ensure_graph(); ASRB_CUDA_CHECK(cudaGraphLaunch(s->step_graph, st)); s->launches += s->graph_B; }
         s->decode_steps += 1; s->greedy_done += 1;

@@ -253,9 +253,9 @@ def test_token_ids_batch_larger_than_8(tiny, tiny_engine):
         assert g == O.transcribe_ids(model, c, max_new_tokens=10).ids
 
 
-def test_long_generation_crosses_fused_step_limit(tiny, tiny_engine):
-    """The fused decode step covers contexts up to 640 keys; a 30 s prompt (405) + 300 new tokens crosses it
-    mid-generation and must continue seamlessly on the per-phase path (same KV cache, same state)."""
+def test_long_generation_beyond_ten_splits(tiny, tiny_engine):
+    """A 30 s prompt (405 keys) + 300 new tokens: the fused decode step runs with up to 12 attention splits of 64
+    cached keys per kv head (contexts up to 1152 keys are covered by 18 splits)."""
     _, _, model = tiny
     x = synth.make_clip(300, 30.0)
     n_new = 300
@@ -264,6 +264,20 @@ def test_long_generation_crosses_fused_step_limit(tiny, tiny_engine):
     assert len(ref.ids) == n_new
     assert got.ids[0] == ref.ids
     assert got.decode_steps == n_new - 1
+
+
+def test_long_generation_crosses_fused_step_limit(tiny, tiny_engine):
+    """The fused decode step covers contexts up to 1152 keys; a 60 s prompt (795) + 400 new tokens crosses it
+    mid-generation and must continue seamlessly on the per-phase path (same KV cache, same state)."""
+    _, _, model = tiny
+    x = synth.make_clip(302, 60.0)
+    n_new = 400
+    ref = O.transcribe_ids(model, x, max_new_tokens=n_new)
+    got = tiny_engine.transcribe_ids([x], max_new_tokens=n_new)
+    assert len(ref.ids) == n_new
+    assert got.ids[0] == ref.ids
+    assert got.decode_steps == n_new - 1
+    assert got.kernels_launched > 2 * got.decode_steps          # the tail ran as per-phase kernels (fused: 1 launch per step)
 
 
 def test_max_new_tokens_one(tiny, tiny_engine):
