@@ -130,7 +130,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN;
-    const int num_kb = K / BK;
+    // split-K: gridDim.z CTAs share one output tile, each contracts num_kb k-blocks starting at kb0 and writes its
+    // partial tile to row block blockIdx.z of a [splits][M][N] fp32 workspace (plain epilogue, see launch_gemm_tc)
+    const int num_kb = K / BK / (int)gridDim.z;
+    const int kb0 = (int)blockIdx.z * num_kb;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -165,7 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             uint8_t* st = smem + s * STAGE_BYTES;
             mbar_expect_tx(&full[s], stage_tx);
             if (A_MODE == 0) {
-                for (int p = 0; p < nplanes; ++p) tma_load_3d(st + p * TILE_A_BYTES, &mapA, kb * BK, m0, p, &full[s]);
+                for (int p = 0; p < nplanes; ++p) tma_load_3d(st + p * TILE_A_BYTES, &mapA, (kb0 + kb) * BK, m0, p, &full[s]);
             } else {
                 const int tap = kb / cg.kblk_per_tap, cb = kb % cg.kblk_per_tap;
                 const int kh = tap / 3, kw = tap % 3;
@@ -174,7 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int p = 0; p < nplanes; ++p)
                     tma_load_5d(st + p * TILE_A_BYTES, &mapA, cb * BK, w, h, (chunk * 2 + ph) * 2 + pw, p, &full[s]);
             }
-            tma_load_2d(st + 3 * TILE_A_BYTES, &mapB, kb * BK, n0, &full[s]);
+            tma_load_2d(st + 3 * TILE_A_BYTES, &mapB, (kb0 + kb) * BK, n0, &full[s]);
         }
     } else if (warp == 1 && lane == 0) {
         // ================= MMA issuer =================
@@ -222,7 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[cb])) : "memory");
         }
         long long m = -1;
-        if (A_MODE == 0) { if (m0 + r < M) m = m0 + r; }
+        if (A_MODE == 0) { if (m0 + r < M) m = m0 + r + (long long)blockIdx.z * M; }
         else {
             const int oh = oh0 + r / cg.OW, ow = r % cg.OW;
             if (r < cg.box_h * cg.OW && oh < cg.OH) m = ((long long)chunk * cg.OH + oh) * cg.OW + ow;
@@ -241,6 +244,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
+}
+
+// split-K second pass: sum the partial tiles in a fixed order, then the GEMM's own epilogue (bias / GELU / residual / split3)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int S, int M, int N, GemmEpi E) {
+    const int n8 = N / 8;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * n8) return;
+    const int m = idx / n8, n = (idx - m * n8) * 8;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    for (int sp = 0; sp < S; ++sp) {
+        const float* src = ws + ((size_t)sp * M + m) * N + n;
+        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    epi_store8<EPI_PLAIN>(E, N, m, n, v);
 }
 
 // ---- host: tensor maps ---------------------------------------------------------------------------
@@ -292,6 +312,29 @@ bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& E, cuda
         cuuint32_t ab[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1};
         CUtensorMap mapA = make_map(A.a, 3, ad, as, ab);
         dim3 grid((N + BN - 1) / BN, (A.M + BM - 1) / BM);
+        // Split-K for plain GEMMs that cannot fill the GPU (e.g. prefill o_proj / down_proj: 32 tiles, K = 2048 / 3072;
+        // encoder fc2: 28 tiles, K = 3584): such a CTA is bound by its own TMA load rate (64 KB of operands per k-block),
+        // so 2-4 CTAs per tile finish 2-4x sooner; a second pass sums the partial tiles (fixed order) and applies the
+        // epilogue.  Deterministic; costs one extra fp32 round trip of the tile through L2.
+        const int tiles = (int)(grid.x * grid.y), kblocks = A.K / BK;
+        int splits = 1;
+        if (E.mode == EPI_PLAIN && E.splitk_ws && tiles <= 64 && N % 8 == 0 && (size_t)4 * A.M * N <= SPLITK_WS_FLOATS) {
+            for (int sp = 4; sp >= 2; --sp)
+                if (kblocks % sp == 0 && kblocks / sp >= 6 && tiles * sp <= 160) { splits = sp; break; }
+        }
+        if (splits > 1) {
+            GemmEpi P;                               // partial tiles: plain fp32 rows [split][M][N]
+            P.out_f32 = E.splitk_ws; P.ldo = N;
+            grid.z = splits;
+            static bool attr_s = false;
+            if (!attr_s) { ASRB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<0, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_s = true; }
+            gemm_tc_kernel<0, EPI_PLAIN><<<grid, NTHREADS, smem, st>>>(mapA, mapB, A.M, N, A.K, A.nplanes, cg, P);
+            const int work = A.M * (N / 8);
+            splitk_reduce_kernel<<<(work + 255) / 256, 256, 0, st>>>(E.splitk_ws, splits, A.M, N, E);
+            ASRB_CUDA_CHECK(cudaGetLastError());
+            if (E.extra_launches) *E.extra_launches += 1;
+            return true;
+        }
 #define ASRB_TC_LAUNCH(AM, EM)                                                                                         \
     {                                                                                                                  \
         static bool attr = false;                                                                                      \

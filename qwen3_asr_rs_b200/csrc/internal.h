@@ -113,7 +113,11 @@ struct GemmEpi {
     const int* row_map = nullptr;     // [M] -> token row or -1
     const float* pos = nullptr;       // [pos_period][N]
     int pos_period = 1;
+    // optional fp32 workspace for split-K (EPI_PLAIN GEMMs with too few tiles to fill the GPU): >= SPLITK_WS_FLOATS floats
+    float* splitk_ws = nullptr;
+    int64_t* extra_launches = nullptr;   // incremented by the number of kernels launched beyond the one GEMM kernel
 };
+static constexpr size_t SPLITK_WS_FLOATS = (size_t)4 * 64 * 128 * 128;   // 4 splits x 64 tiles of 128 x 128
 enum { GEMM_SIMT = 0, GEMM_TC = 1 };
 void launch_gemm(const GemmA& A, const bf16* W, int N, const GemmEpi& E, int impl, cudaStream_t st);
 // tcgen05 implementation (gemm_tc.cu); returns false when the shape is unsupported

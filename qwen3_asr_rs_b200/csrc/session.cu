@@ -46,6 +46,7 @@ struct Session {
     bf16 *dh = nullptr, *dattn = nullptr, *dact = nullptr; size_t dh_ps = 0, dattn_ps = 0, dact_ps = 0;
     float *kcache = nullptr, *vcache = nullptr; size_t cache_layer_stride = 0, cache_seq_stride = 0;
     DecodeBufs db{};
+    float* splitk_ws = nullptr;   // fp32 partial tiles of split-K GEMMs (gemm_tc.cu)
     MegaBufs mega{};
     unsigned mega_steps = 1;   // host mirror of the device epoch (upper bound): see launch_decode_step_mega
     int* d_lastrow = nullptr;
@@ -132,6 +133,7 @@ Session* session_create(Model* m, int max_batch, int64_t max_samples, int max_la
         s->enc_h = salloc<bf16>(s, 3 * s->ench_ps);
         s->enc_attn = salloc<bf16>(s, 3 * s->ench_ps);
         s->enc_ff = salloc<bf16>(s, 3 * s->encff_ps);
+        s->splitk_ws = salloc<float>(s, SPLITK_WS_FLOATS);
         // decoder activations
         s->hid = salloc<float>(s, totS * c.hidden_size);
         s->dqkv = salloc<float>(s, totS * d.qkv_dim);
@@ -302,14 +304,14 @@ void session_encode(Session* s, int64_t* n_tokens_out) {
           p.causal = 0; p.max_len = maxwin; p.out_s3 = s->enc_attn; p.plane_stride = s->ench_ps; p.ldo = dm;
           launch_attention(p, d.enc_hd, st); }
         { GemmA A = plainA(s->enc_attn, s->ench_ps, totT, dm, np);
-          GemmEpi E; E.bias = w.bo; E.residual = s->x_enc; E.ldr = dm; E.out_f32 = s->x_enc; E.ldo = dm;
+          GemmEpi E; E.bias = w.bo; E.residual = s->x_enc; E.ldr = dm; E.out_f32 = s->x_enc; E.ldo = dm; E.splitk_ws = s->splitk_ws; E.extra_launches = &s->launches;
           launch_gemm(A, w.wo, dm, E, s->gemm_impl, st); }
         launch_layernorm_s3(s->x_enc, w.ln2_w, w.ln2_b, totT, dm, 1e-5f, s->enc_h, s->ench_ps, st);
         { GemmA A = plainA(s->enc_h, s->ench_ps, totT, dm, np);
           GemmEpi E; E.bias = w.b1; E.act = 1; E.out_s3 = s->enc_ff; E.s3_plane_stride = s->encff_ps; E.lds = c.encoder_ffn_dim;
           launch_gemm(A, w.fc1, c.encoder_ffn_dim, E, s->gemm_impl, st); }
         { GemmA A = plainA(s->enc_ff, s->encff_ps, totT, c.encoder_ffn_dim, np);
-          GemmEpi E; E.bias = w.b2; E.residual = s->x_enc; E.ldr = dm; E.out_f32 = s->x_enc; E.ldo = dm;
+          GemmEpi E; E.bias = w.b2; E.residual = s->x_enc; E.ldr = dm; E.out_f32 = s->x_enc; E.ldo = dm; E.splitk_ws = s->splitk_ws; E.extra_launches = &s->launches;
           launch_gemm(A, w.fc2, dm, E, s->gemm_impl, st); }
         s->launches += 7;
     }
@@ -319,7 +321,7 @@ void session_encode(Session* s, int64_t* n_tokens_out) {
       GemmEpi E; E.bias = m.proj1_b; E.act = 1; E.out_s3 = s->enc_attn; E.s3_plane_stride = s->ench_ps; E.lds = dm;
       launch_gemm(A, m.proj1, dm, E, s->gemm_impl, st); }
     { GemmA A = plainA(s->enc_attn, s->ench_ps, totT, dm, np);
-      GemmEpi E; E.bias = m.proj2_b; E.out_f32 = s->audio; E.ldo = c.output_dim;
+      GemmEpi E; E.bias = m.proj2_b; E.out_f32 = s->audio; E.ldo = c.output_dim; E.splitk_ws = s->splitk_ws; E.extra_launches = &s->launches;
       launch_gemm(A, m.proj2, c.output_dim, E, s->gemm_impl, st); }
     s->launches += 3;
     if (n_tokens_out) for (int b = 0; b < B; ++b) n_tokens_out[b] = s->T[b];
@@ -399,14 +401,14 @@ void session_prefill(Session* s, const int64_t* const* lang_ids, const int32_t* 
           p.out_s3 = s->dattn; p.plane_stride = s->dattn_ps; p.ldo = d.q_dim;
           launch_attention(p, c.head_dim, st); }
         { GemmA A = plainA(s->dattn, s->dattn_ps, totS, d.q_dim, np);
-          GemmEpi E; E.residual = s->hid; E.ldr = H; E.out_f32 = s->hid; E.ldo = H;
+          GemmEpi E; E.residual = s->hid; E.ldr = H; E.out_f32 = s->hid; E.ldo = H; E.splitk_ws = s->splitk_ws; E.extra_launches = &s->launches;
           launch_gemm(A, w.wo, H, E, s->gemm_impl, st); }
         launch_rmsnorm_s3(s->hid, w.ln_post, totS, H, eps, s->dh, s->dh_ps, st);
         { GemmA A = plainA(s->dh, s->dh_ps, totS, H, np);
           GemmEpi E; E.mode = EPI_SWIGLU; E.out_s3 = s->dact; E.s3_plane_stride = s->dact_ps; E.lds = c.intermediate_size;
           launch_gemm(A, w.wgu, 2 * c.intermediate_size, E, s->gemm_impl, st); }
         { GemmA A = plainA(s->dact, s->dact_ps, totS, c.intermediate_size, np);
-          GemmEpi E; E.residual = s->hid; E.ldr = H; E.out_f32 = s->hid; E.ldo = H;
+          GemmEpi E; E.residual = s->hid; E.ldr = H; E.out_f32 = s->hid; E.ldo = H; E.splitk_ws = s->splitk_ws; E.extra_launches = &s->launches;
           launch_gemm(A, w.wdown, H, E, s->gemm_impl, st); }
         s->launches += 8;
     }
