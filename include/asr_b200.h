@@ -133,7 +133,13 @@ ASRB_API int asrb_generate(asrb_session* s, int max_new_tokens, int32_t* ids_out
  * plus counters (kernels launched, decoder forward steps) */
 ASRB_API int asrb_last_timings(asrb_session* s, float* ms_out6, int64_t* kernels_launched,
                       int64_t* decode_steps);
-/* knobs: "gemm" = "tc"|"simt", "decode" = "mega"|"phases", "planes" = "1"|"2"|"3",
+/* Path counters since session creation -- silent fallbacks made visible (bench.py asserts the fallback ones are 0):
+ *   [0] decoder forwards on the batch-aware fused step   [1] on the single-sequence fused step
+ *   [2] on the per-phase kernels (fallback: logits requested, unsupported dims, context beyond the fused limit)
+ *   [3] GEMMs that fell back from tcgen05 to the SIMT kernel (process-wide)   [4] tcgen05 GEMM launches (process-wide)
+ * writes min(n, 5) values */
+ASRB_API int asrb_session_stats(asrb_session* s, int64_t* out, int n);
+/* knobs: "gemm" = "tc"|"simt", "decode" = "mega"|"phases", "batch_step" = "1"|"0", "planes" = "1"|"2"|"3",
  * "resident" = "1"|"0" (1: the samples uploaded by the previous call are reused, no H2D) */
 ASRB_API int asrb_session_set_option(asrb_session* s, const char* key, const char* value);
 

@@ -23,6 +23,7 @@ void session_transcribe_ids(Session* s, const float* const* samples, const int64
                             int32_t* ids_out, int32_t* lens_out);
 void session_last_timings(Session* s, float* ms6, int64_t* kernels, int64_t* steps);
 void session_set_option(Session* s, const char* key, const char* value);
+void session_stats(Session* s, int64_t* out, int n);
 int decode_mega_debug_timeline(long long* out, int cap);
 }  // namespace asrb
 
@@ -147,6 +148,9 @@ int asrb_generate(asrb_session* s, int max_new_tokens, int32_t* ids_out, int32_t
 }
 int asrb_last_timings(asrb_session* s, float* ms_out6, int64_t* kernels_launched, int64_t* decode_steps) {
     return guarded([&] { NONNULL(s); session_last_timings(s->s, ms_out6, kernels_launched, decode_steps); });
+}
+int asrb_session_stats(asrb_session* s, int64_t* out, int n) {
+    return guarded([&] { NONNULL(s); NONNULL(out); session_stats(s->s, out, n); });
 }
 int asrb_session_set_option(asrb_session* s, const char* key, const char* value) {
     return guarded([&] { NONNULL(s); session_set_option(s->s, key, value); });

@@ -66,8 +66,13 @@ void launch_gemm_simt(const GemmA& A, const bf16* W, int N, const GemmEpi& E, cu
     ASRB_CUDA_CHECK(cudaGetLastError());
 }
 
+std::atomic<int64_t> g_gemm_simt_fallbacks{0}, g_gemm_tc_launches{0};
+
 void launch_gemm(const GemmA& A, const bf16* W, int N, const GemmEpi& E, int impl, cudaStream_t st) {
-    if (impl == GEMM_TC && launch_gemm_tc(A, W, N, E, st)) return;
+    if (impl == GEMM_TC) {
+        if (launch_gemm_tc(A, W, N, E, st)) { g_gemm_tc_launches += 1; return; }
+        g_gemm_simt_fallbacks += 1;        // counted, never silent: asrb_session_stats()[3] (bench.py requires 0)
+    }
     launch_gemm_simt(A, W, N, E, st);
 }
 

@@ -1,5 +1,6 @@
 // internal.h -- host-side structures and kernel launch prototypes (not part of the ABI).
 #pragma once
+#include <atomic>
 #include <map>
 #include <string>
 #include <vector>
@@ -119,6 +120,7 @@ struct GemmEpi {
 };
 static constexpr size_t SPLITK_WS_FLOATS = (size_t)4 * 64 * 128 * 128;   // 4 splits x 64 tiles of 128 x 128
 enum { GEMM_SIMT = 0, GEMM_TC = 1 };
+extern std::atomic<int64_t> g_gemm_simt_fallbacks, g_gemm_tc_launches;   // gemm_simt.cu: tcgen05 requested but SIMT ran / tcgen05 launches
 void launch_gemm(const GemmA& A, const bf16* W, int N, const GemmEpi& E, int impl, cudaStream_t st);
 // tcgen05 implementation (gemm_tc.cu); returns false when the shape is unsupported
 bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& E, cudaStream_t st);
@@ -181,6 +183,8 @@ void launch_decode_step_phases(const Model& m, const DecodeBufs& b, int B, float
 // also performs the greedy bookkeeping of src/inference.rs:161-170 (EOS check, append, embed)
 struct MegaBufs { unsigned* bar = nullptr; float* part = nullptr; long long* dbg = nullptr; size_t part_bytes = 0; unsigned* steps_issued = nullptr; };   // per-session state of the fused step
 size_t decode_mega_part_floats(const Model& m);
+size_t decode_batch_part_floats(const Model& m);   // decode_batch.cu: NB sequences per fused launch
+bool decode_batch_supported(const Model& m, int B, int ctx);
 int decode_mega_dbg_slots();
 void launch_greedy(const Model& m, const DecodeBufs& b, int B, cudaStream_t st, int64_t* launches);
 void launch_lmhead_argmax(const Model& m, const float* x_rows, const int* d_row_idx, int B,

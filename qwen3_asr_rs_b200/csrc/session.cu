@@ -25,6 +25,8 @@ struct Session {
     int maxF = 0, maxC = 0, maxT = 0, maxS = 0, max_ctx = 0;
     int gemm_impl = GEMM_TC;
     int decode_mode = 1;   // 1 = fused step when available, 0 = per-phase kernels
+    bool batch_step = true;   // batch >= 2: the batch-aware fused step (decode_batch.cu); false = one fused launch per sequence
+    int64_t n_batch_steps = 0, n_mega_steps = 0, n_phase_steps = 0;   // decoder forwards by path since session creation
     int nplanes = 3;
     // ---- current batch plan (host) ----
     int stage = 0;         // 0 idle, 1 mel, 2 encoded, 3 prefilled
@@ -162,8 +164,9 @@ Session* session_create(Model* m, int max_batch, int64_t max_samples, int max_la
         s->d_lastrow = salloc<int>(s, Bm);
         s->mega.bar = salloc<unsigned>(s, 4, true);
         { const unsigned one = 1; ASRB_CUDA_CHECK(cudaMemcpy(s->mega.bar + 1, &one, sizeof(one), cudaMemcpyHostToDevice)); }   // epoch 1
-        s->mega.part = salloc<float>(s, decode_mega_part_floats(*m), true);   // zero = tag 0 = never written
-        s->mega.part_bytes = decode_mega_part_floats(*m) * sizeof(float);
+        const size_t part_floats = std::max(decode_mega_part_floats(*m), decode_batch_part_floats(*m));
+        s->mega.part = salloc<float>(s, part_floats, true);   // zero = tag 0 = never written
+        s->mega.part_bytes = part_floats * sizeof(float);
         s->mega.steps_issued = &s->mega_steps;
         if (getenv("ASRB_MEGA_DEBUG")) s->mega.dbg = salloc<long long>(s, decode_mega_dbg_slots(), true);
         ASRB_CUDA_CHECK(cudaMallocHost(&s->h_done, Bm * sizeof(int)));
@@ -430,6 +433,11 @@ void session_prefill(Session* s, const int64_t* const* lang_ids, const int32_t* 
 // step 8: greedy loop  (inference.rs:160-200)
 // -------------------------------------------------------------------------------------------------
 bool decode_mega_supported(const Model& m, int B, int max_ctx);
+bool decode_batch_supported(const Model& m, int B, int max_ctx);
+size_t decode_batch_part_floats(const Model& m);
+void launch_decode_step_batch(const Model& m, const DecodeBufs& b, int B, float* kcache, float* vcache,
+                              size_t cache_layer_stride, size_t cache_seq_stride, int max_ctx, int ctx_now, const MegaBufs& mb,
+                              cudaStream_t st, int64_t* launches);
 void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* kcache, float* vcache,
                              size_t cache_layer_stride, size_t cache_seq_stride, int max_ctx, int ctx_now, const MegaBufs& mb,
                              cudaStream_t st, int64_t* launches);
@@ -440,15 +448,25 @@ int decode_mega_dbg_slots();
 // that selects / appends / embeds the next one.  (The fused kernel does both.)
 // upper bound of (position + 1) for the next forward: prompt length + tokens appended so far
 static int ctx_bound(const Session* s) { return std::min(s->max_ctx, s->maxlenS + s->greedy_done); }
+static bool use_batch(Session* s, bool write_logits) {     // batch >= 2: weights streamed once for all sequences
+    return s->decode_mode == 1 && s->batch_step && !write_logits && s->B >= 2 && decode_batch_supported(*s->m, s->B, ctx_bound(s));
+}
 static bool use_mega(Session* s, bool write_logits) {
-    return s->decode_mode == 1 && !write_logits && decode_mega_supported(*s->m, s->B, ctx_bound(s));
+    return use_batch(s, write_logits) ||
+           (s->decode_mode == 1 && !write_logits && decode_mega_supported(*s->m, s->B, ctx_bound(s)));
 }
 static void forward_step(Session* s, bool write_logits) {
     Model& m = *s->m;
-    if (use_mega(s, write_logits)) {
+    if (use_batch(s, write_logits)) {
+        launch_decode_step_batch(m, s->db, s->B, s->kcache, s->vcache, s->cache_layer_stride, s->cache_seq_stride, s->max_ctx,
+                                 ctx_bound(s), s->mega, s->st, &s->launches);
+        s->n_batch_steps += 1;
+    } else if (use_mega(s, write_logits)) {
         launch_decode_step_mega(m, s->db, s->B, s->kcache, s->vcache, s->cache_layer_stride, s->cache_seq_stride, s->max_ctx,
                                 ctx_bound(s), s->mega, s->st, &s->launches);
+        s->n_mega_steps += 1;
     } else {
+        s->n_phase_steps += 1;
         launch_decode_step_phases(m, s->db, s->B, s->kcache, s->vcache, s->cache_layer_stride, s->cache_seq_stride, s->max_ctx,
                                   write_logits, s->st, &s->launches);
         launch_greedy(m, s->db, s->B, s->st, &s->launches);
@@ -546,6 +564,11 @@ void session_last_timings(Session* s, float* ms6, int64_t* kernels, int64_t* ste
     if (steps) *steps = s->decode_steps;
 }
 
+void session_stats(Session* s, int64_t* out, int n) {
+    const int64_t v[5] = {s->n_batch_steps, s->n_mega_steps, s->n_phase_steps, g_gemm_simt_fallbacks.load(), g_gemm_tc_launches.load()};
+    for (int i = 0; i < n && i < 5; ++i) out[i] = v[i];
+}
+
 void session_set_option(Session* s, const char* key, const char* value) {
     std::string k(key ? key : ""), v(value ? value : "");
     if (k == "gemm") {
@@ -554,6 +577,8 @@ void session_set_option(Session* s, const char* key, const char* value) {
     } else if (k == "decode") {
         if (v == "mega") s->decode_mode = 1; else if (v == "phases") s->decode_mode = 0;
         else throw Error(ASRB_ERR_INVALID, "decode must be mega|phases");
+    } else if (k == "batch_step") {
+        s->batch_step = (v == "1");
     } else if (k == "planes") {
         int p = atoi(v.c_str());
         ASRB_REQUIRE(p >= 1 && p <= 3, ASRB_ERR_INVALID, "planes must be 1..3");

@@ -144,6 +144,15 @@ class AsrInference:
         if self._session is not None:
             _lib.check(self._lib.asrb_session_set_option(self._session, key.encode(), value.encode()))
 
+    def stats(self) -> Dict[str, int]:
+        """Decoder-forward / GEMM path counters (asrb_session_stats): fallbacks are visible, never silent."""
+        out = (C.c_int64 * 5)()
+        if self._session is None:
+            return {}
+        _lib.check(self._lib.asrb_session_stats(self._session, out, 5))
+        return dict(zip(("decode_batch_steps", "decode_fused_steps", "decode_phase_steps", "gemm_simt_fallbacks",
+                         "gemm_tc_launches"), [int(v) for v in out]))
+
     def _ensure_session(self, batch: int, max_samples: int, max_lang: int, max_new: int):
         cap = self._cap
         if cap is None or batch > cap[0] or max_samples > cap[1] or max_lang > cap[2] or max_new > cap[3]:

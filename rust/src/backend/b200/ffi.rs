@@ -58,6 +58,7 @@ extern "C" {
     pub fn asrb_generate(s: *mut asrb_session, max_new_tokens: c_int, ids_out: *mut i32, lens_out: *mut i32) -> c_int;
 
     pub fn asrb_last_timings(s: *mut asrb_session, ms_out6: *mut f32, kernels_launched: *mut i64, decode_steps: *mut i64) -> c_int;
+    pub fn asrb_session_stats(s: *mut asrb_session, out: *mut i64, n: c_int) -> c_int;
     pub fn asrb_session_set_option(s: *mut asrb_session, key: *const c_char, value: *const c_char) -> c_int;
     pub fn asrb_debug_mega_timeline(out: *mut c_longlong, cap: c_int) -> c_int;
 }
