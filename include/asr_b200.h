@@ -84,6 +84,10 @@ ASRB_API int asrb_model_set_tensor(asrb_model* m, const char* name, int dtype,
                           const int64_t* shape, int ndim, const void* host_data);
 ASRB_API int asrb_model_finalize(asrb_model* m);
 ASRB_API int asrb_model_dims(const asrb_model* m, asrb_dims* out);
+/* Matrices are kept in bf16 (lossless for the released bf16 checkpoints; the reference widens them to f32,
+ * src/weights.rs:74-89).  An F32/F16 matrix that is not bf16-representable is REJECTED by set_tensor / load unless
+ * ASRB_ALLOW_LOSSY_WEIGHTS=1; *count = number of matrices that were rounded under that override (0 = exact). */
+ASRB_API int asrb_model_lossy_tensors(const asrb_model* m, int* count);
 ASRB_API int asrb_model_free(asrb_model* m);
 
 /* ---- session --------------------------------------------------------------------- */
@@ -133,6 +137,12 @@ ASRB_API int asrb_generate(asrb_session* s, int max_new_tokens, int32_t* ids_out
  * plus counters (kernels launched, decoder forward steps) */
 ASRB_API int asrb_last_timings(asrb_session* s, float* ms_out6, int64_t* kernels_launched,
                       int64_t* decode_steps);
+/* Device-resident results of the last asrb_generate / asrb_transcribe_ids (valid until the next call on this
+ * session; the session stream has been synchronised): ids [max_batch][max_new_tokens] int32 and lens [max_batch]
+ * int32 in HBM.  This is what the multi-GPU gather (the path's only collective: one all-gather of ids over
+ * NCCL / NVLink) reads directly, with no host staging. */
+ASRB_API int asrb_session_device_ids(asrb_session* s, const int32_t** ids_dev, const int32_t** lens_dev,
+                            int* row_stride, int* batch);
 /* Path counters since session creation -- silent fallbacks made visible (bench.py asserts the fallback ones are 0):
  *   [0] decoder forwards on the batch-aware fused step   [1] on the single-sequence fused step
  *   [2] on the per-phase kernels (fallback: logits requested, unsupported dims, context beyond the fused limit)

@@ -15,7 +15,7 @@ SYMBOLS = [
     "asrb_model_dims", "asrb_model_free", "asrb_session_create", "asrb_session_free",
     "asrb_transcribe_ids", "asrb_mel", "asrb_mel_read", "asrb_encode", "asrb_encode_read",
     "asrb_prefill", "asrb_decode_step", "asrb_generate", "asrb_last_timings", "asrb_session_set_option",
-    "asrb_debug_mega_timeline", "asrb_session_stats",
+    "asrb_debug_mega_timeline", "asrb_session_stats", "asrb_session_device_ids", "asrb_model_lossy_tensors",
 ]
 
 
@@ -60,6 +60,7 @@ def load_library() -> C.CDLL:
         "asrb_model_finalize": [vp],
         "asrb_model_dims": [vp, P(AsrbDims)],
         "asrb_model_free": [vp],
+        "asrb_model_lossy_tensors": [vp, P(C.c_int)],
         "asrb_session_create": [vp, C.c_int, i64, C.c_int, C.c_int, P(vp)],
         "asrb_session_free": [vp],
         "asrb_transcribe_ids": [vp, P(P(C.c_float)), P(i64), C.c_int, P(P(i64)), P(i32), C.c_int, P(i32), P(i32)],
@@ -74,6 +75,7 @@ def load_library() -> C.CDLL:
         "asrb_session_set_option": [vp, C.c_char_p, C.c_char_p],
         "asrb_debug_mega_timeline": [P(C.c_longlong), C.c_int],
         "asrb_session_stats": [vp, P(i64), C.c_int],
+        "asrb_session_device_ids": [vp, P(vp), P(vp), P(C.c_int), P(C.c_int)],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

@@ -127,13 +127,11 @@ void launch_attention(const AttnParams& p, int hd, cudaStream_t st) {
     dim3 grid((p.max_len + QT - 1) / QT, p.nheads, p.nseg);
     if (hd == 64) {
         size_t smem = (QT * 65 + KT * 65 + KT * 64 + QT * KT) * sizeof(float);
-        static bool attr64 = false;
-        if (!attr64) { ASRB_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr64 = true; }
+        ASRB_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set on every launch
         attn_kernel<64><<<grid, ATT_THREADS, smem, st>>>(p);
     } else if (hd == 128) {
         size_t smem = (QT * 129 + KT * 129 + KT * 128 + QT * KT) * sizeof(float);
-        static bool attr128 = false;
-        if (!attr128) { ASRB_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr128 = true; }
+        ASRB_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set on every launch
         attn_kernel<128><<<grid, ATT_THREADS, smem, st>>>(p);
     } else {
         throw Error(ASRB_ERR_INVALID, "attention head_dim must be 64 or 128");

@@ -208,12 +208,10 @@ bool launch_attention_f32(const AttnParams& p, int hd, cudaStream_t st) {
     const int nqt_max = (p.max_len + QT - 1) / QT;
     dim3 grid(p.causal ? (nqt_max + 1) / 2 : nqt_max, p.nheads, p.nseg);
     if (hd == 64) {
-        static bool attr = false;
-        if (!attr) { ASRB_CUDA_CHECK(cudaFuncSetAttribute(attn_f32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<64>())); attr = true; }
+        ASRB_CUDA_CHECK(cudaFuncSetAttribute(attn_f32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<64>()));   // per device: set on every launch
         attn_f32_kernel<64><<<grid, THREADS, smem_bytes<64>(), st>>>(p);
     } else if (hd == 128) {
-        static bool attr = false;
-        if (!attr) { ASRB_CUDA_CHECK(cudaFuncSetAttribute(attn_f32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<128>())); attr = true; }
+        ASRB_CUDA_CHECK(cudaFuncSetAttribute(attn_f32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<128>()));   // per device: set on every launch
         attn_f32_kernel<128><<<grid, THREADS, smem_bytes<128>(), st>>>(p);
     } else return false;
     ASRB_CUDA_CHECK(cudaGetLastError());

@@ -193,12 +193,10 @@ bool launch_attention_tc(const AttnParams& p, int hd, cudaStream_t st) {
     if ((p.ldq % 4) || (p.ldk % 4) || (p.head_stride % 4) || (p.seg_stride % 4)) return false;
     dim3 grid((p.max_len + QT - 1) / QT, p.nheads, p.nseg);
     if (hd == 64) {
-        static bool attr = false;
-        if (!attr) { ASRB_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<64>())); attr = true; }
+        ASRB_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<64>()));   // per device: set on every launch
         attn_tc_kernel<64><<<grid, THREADS, smem_bytes<64>(), st>>>(p);
     } else if (hd == 128) {
-        static bool attr = false;
-        if (!attr) { ASRB_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<128>())); attr = true; }
+        ASRB_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<128>()));   // per device: set on every launch
         attn_tc_kernel<128><<<grid, THREADS, smem_bytes<128>(), st>>>(p);
     } else return false;
     ASRB_CUDA_CHECK(cudaGetLastError());

@@ -24,10 +24,27 @@ void session_transcribe_ids(Session* s, const float* const* samples, const int64
 void session_last_timings(Session* s, float* ms6, int64_t* kernels, int64_t* steps);
 void session_set_option(Session* s, const char* key, const char* value);
 void session_stats(Session* s, int64_t* out, int n);
+void session_device_ids(Session* s, const int32_t** ids, const int32_t** lens, int* stride, int* batch);
 int decode_mega_debug_timeline(long long* out, int cap);
+int decode_batch_debug_timeline(long long* out, int cap);
 }  // namespace asrb
 
 using namespace asrb;
+
+namespace asrb {
+// shared by asrb_model_create and the config.json loader: anything that would divide by zero or index out of bounds later
+void validate_dims(const asrb_dims& d) {
+    ASRB_REQUIRE(d.num_mel_bins == 128, ASRB_ERR_INVALID, "num_mel_bins must be 128");
+    ASRB_REQUIRE(d.n_window > 0 && d.n_window_infer > 0 && d.d_model > 0 && d.encoder_layers > 0 && d.encoder_attention_heads > 0 &&
+                     d.d_model % d.encoder_attention_heads == 0 && d.encoder_ffn_dim > 0 && d.downsample_hidden_size > 0 && d.output_dim > 0,
+                 ASRB_ERR_INVALID, "bad audio encoder dims");
+    ASRB_REQUIRE(d.hidden_size > 0 && d.intermediate_size > 0 && d.num_hidden_layers > 0 && d.num_attention_heads > 0 &&
+                     d.num_key_value_heads > 0 && d.num_attention_heads % d.num_key_value_heads == 0 && d.head_dim > 0 && d.head_dim % 2 == 0,
+                 ASRB_ERR_INVALID, "bad text decoder dims");
+    ASRB_REQUIRE(d.vocab_size > 151676, ASRB_ERR_INVALID, "bad dims (vocab must contain the prompt special tokens)");
+    ASRB_REQUIRE(d.rms_norm_eps > 0 && d.rope_theta > 1.0, ASRB_ERR_INVALID, "bad rms_norm_eps / rope_theta");
+}
+}  // namespace asrb
 
 static thread_local std::string g_last_error;
 
@@ -84,9 +101,7 @@ int asrb_dims_default(asrb_dims* d) {
 int asrb_model_create(asrb_ctx* ctx, const asrb_dims* dims, asrb_model** out) {
     return guarded([&] {
         NONNULL(ctx); NONNULL(dims); NONNULL(out);
-        ASRB_REQUIRE(dims->num_mel_bins == 128, ASRB_ERR_INVALID, "num_mel_bins must be 128");
-        ASRB_REQUIRE(dims->n_window > 0 && dims->d_model > 0 && dims->hidden_size > 0 && dims->vocab_size > 151676,
-                     ASRB_ERR_INVALID, "bad dims (vocab must contain the prompt special tokens)");
+        validate_dims(*dims);
         ASRB_CUDA_CHECK(cudaSetDevice(ctx->c.device));
         asrb_model* m = new asrb_model();
         m->m.ctx = &ctx->c; m->m.d.c = *dims; m->m.d.derive();
@@ -113,6 +128,7 @@ int asrb_model_load(asrb_ctx* ctx, const char* model_dir, asrb_model** out) {
     });
 }
 int asrb_model_dims(const asrb_model* m, asrb_dims* out) { return guarded([&] { NONNULL(m); NONNULL(out); *out = m->m.d.c; }); }
+int asrb_model_lossy_tensors(const asrb_model* m, int* count) { return guarded([&] { NONNULL(m); NONNULL(count); *count = m->m.lossy_count; }); }
 int asrb_model_free(asrb_model* m) { return guarded([&] { if (m) { cudaSetDevice(m->m.ctx->device); delete m; } }); }
 
 int asrb_session_create(asrb_model* m, int max_batch, int64_t max_samples, int max_lang_ids, int max_new_tokens, asrb_session** out) {
@@ -149,6 +165,10 @@ int asrb_generate(asrb_session* s, int max_new_tokens, int32_t* ids_out, int32_t
 int asrb_last_timings(asrb_session* s, float* ms_out6, int64_t* kernels_launched, int64_t* decode_steps) {
     return guarded([&] { NONNULL(s); session_last_timings(s->s, ms_out6, kernels_launched, decode_steps); });
 }
+int asrb_session_device_ids(asrb_session* s, const int32_t** ids_dev, const int32_t** lens_dev, int* row_stride, int* batch) {
+    return guarded([&] { NONNULL(s); NONNULL(ids_dev); NONNULL(lens_dev); NONNULL(row_stride); NONNULL(batch);
+                         session_device_ids(s->s, ids_dev, lens_dev, row_stride, batch); });
+}
 int asrb_session_stats(asrb_session* s, int64_t* out, int n) {
     return guarded([&] { NONNULL(s); NONNULL(out); session_stats(s->s, out, n); });
 }
@@ -158,7 +178,8 @@ int asrb_session_set_option(asrb_session* s, const char* key, const char* value)
 
 int asrb_debug_mega_timeline(long long* out, int cap) {
     int n = 0;
-    guarded([&] { n = decode_mega_debug_timeline(out, cap); });
+    guarded([&] { n = (getenv("ASRB_MEGA_DEBUG") && std::string(getenv("ASRB_MEGA_DEBUG")) == "batch") ? decode_batch_debug_timeline(out, cap)
+                                                                                                            : decode_mega_debug_timeline(out, cap); });
     return n;
 }
 

@@ -300,11 +300,8 @@ void launch_decode_step_phases(const Model& m, const DecodeBufs& ball, int Ball,
     const int sms = m.ctx->sm_count;
     const int group = c.num_attention_heads / c.num_key_value_heads;
     size_t attn_smem = (size_t)(group * 128 + group * max_ctx) * sizeof(float);
-    static size_t attn_smem_set = 0;
-    if (attn_smem > 48 * 1024 && attn_smem > attn_smem_set) {
+    if (attn_smem > 48 * 1024)     // per device attribute: set on every launch (a process may drive several GPUs)
         ASRB_CUDA_CHECK(cudaFuncSetAttribute(dec_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
-        attn_smem_set = attn_smem;
-    }
     for (int b0 = 0; b0 < Ball; b0 += 8) {           // sub-batches of 8 sequences (weights are re-streamed per sub-batch)
       const int B = std::min(8, Ball - b0);
       const DecodeBufs b = offset_bufs(ball, b0, m);

@@ -6,12 +6,19 @@
 // CTA's row slice of every weight matrix through a shared-memory ring with cp.async.bulk + mbarrier, 8 consumer
 // warps, {value, tag} words published with fire-and-forget red.max and polled by the consumers (no grid barriers).
 // What changes with a batch:
-//   * activations live in shared memory as xs[NB][H] (RMSNorm applied once when the vector is gathered); a warp
-//     "unit" contracts 4 weight rows against 8 sequences with packed fp32 FMAs (FFMA2: weights are up-cast once per
-//     256-element chunk and reused for 8 sequences, every activation LDS.128 is reused for 4 rows); the 32 sums of
-//     a unit are reduced across the warp with one transposing butterfly (31 shuffles).
+//   * the GEMVs become skinny GEMMs [16 weight rows] x [NB sequences] on the tensor cores: fp32 CUDA-core FMAs cost
+//     rows x K x NB / 64 cycles per SM (measured: FFMA2 issues every ~4 cycles per scheduler), i.e. 265 us per step at
+//     NB = 8 -- more than the HBM time of the whole step.  Activations are written into shared memory as THREE bf16
+//     planes (hi + mid + lo == x to 1 ulp, common.cuh: bf16 x bf16 products are exact in fp32), weights are bf16
+//     already, so mma.sync.m16n8k16 with fp32 accumulation reproduces the fp32 GEMV to accumulation-order noise.  A
+//     16-row tile is contracted by all 8 warps (each takes 1/8 of K: at most 384 products per accumulator, which also
+//     keeps the tensor core's truncating accumulation below the noise floor), partial tiles are summed through
+//     shared memory in a fixed order.  The tile shape follows the CTA's row slice (7 .. 42 rows per matrix), which is
+//     why this is the warp-level MMA and not a 128-row tcgen05 tile; the MMAs are < 3 % of the step either way.
+//     Weight rows are read from a copy whose 16-byte chunks are XOR-swizzled by (row & 7) (model.cu), so that the
+//     bulk-copied rows (2 KB pitch) are bank-conflict free for ldmatrix.
 //   * o_proj / down_proj (7 rows per CTA, K = 2048 / 3072) keep their rows resident in the ring and walk K in
-//     chunks of H (the capacity of xs); their units split K across warps and combine through shared memory.
+//     chunks of H (the capacity of the activation planes).
 //   * attention work items are (sequence, kv head, KVK-key split of the CACHED keys), dealt round-robin to the
 //     CTAs; K and V tiles travel through a two-slot shared-memory stage that the producer refills while the
 //     consumers compute; one CTA per (sequence, kv head) merges the partials, folds in the current token's own
@@ -30,12 +37,13 @@ using namespace mega;
 
 static constexpr int MAXSPLIT = 32;       // partial records per (sequence, kv head): lanes of the merging warps
 static constexpr int MAXROWS = 8;         // residual rows owned by one CTA (H / gridDim.x rounded up)
+static constexpr int ATT_SCRATCH = 4 * HD + NCONS_WARPS * 2 * HD + NCONS_WARPS * 4 + 8;   // q[2][128] k v, per-warp partials
 
 struct Params {
-    const DecLayerW* layers;     // device array [L]; ln_in / ln_post in the xs_swz layout
+    const DecLayerW* layers;     // device array [L]: weight matrices = the chunk-swizzled copies (model.cu), norm vectors plain
     const bf16* lm_head;
     const bf16* embed;
-    const float* final_norm;     // xs_swz layout
+    const float* final_norm;
     const float* rope_cos; const float* rope_sin;
     float eps;
     int L, H, QD, KVD, I, V, nkv;
@@ -45,7 +53,9 @@ struct Params {
     float* part_val; int* part_idx; int n_part;     // [nb][n_part] argmax partials (first gridDim.x used)
     int* pos; int* done; int* next_id; int* ids_out; int* n_out; int max_new;
     unsigned* bar;               // [0] finish ticket, [1] launch epoch
-    uint2* qkv_ll; uint2* part_ll; uint2* attn_ll; uint2* x_ll; uint2* act_ll;
+    uint2* qkv_ll; uint2* part_ll;      // tagged {value, tag} words (few readers per word)
+    uint32_t* sx;                        // self-validating 4-byte words [2 sets][L][XO | XD | ATTN | ACT][NB][rows]
+    long long* dbg;              // optional timeline [2][DBG_SLOTS] of clock64 (CTA 0 and CTA G-1), else null
 };
 
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
@@ -59,71 +69,67 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
-// packed fp32 FMA (FFMA2): d = a * b + c on both halves
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-    float2 d;
-    asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
-        "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd; }"
-        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-    return d;
+// ---- warp-level tensor-core pieces ---------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
-
-// 32 per-lane partial sums -> lane L ends with the warp total of value L (tree: xor 16, 8, 4, 2, 1 -- the tree of
-// warp_sum / row_dot2 of the single-sequence kernel)
-__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-    for (int o = 16, n = 32; n > 1; o >>= 1, n >>= 1) {
-        const bool up = lane & o;
-#pragma unroll
-        for (int i = 0; i < n / 2; ++i) {
-            const float send = up ? v[i] : v[i + n / 2];
-            const float keep = up ? v[i + n / 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
-    }
-    return v[0];
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// 16-byte chunk c of a row whose chunks are XOR-swizzled by `key` (low 3 bits) inside every 128-byte group
+__device__ __forceinline__ int swz16(int c, int key) { return (c & ~7) | ((c ^ key) & 7); }
 
-// One unit: 4 weight rows x 8 sequences over NSUB 256-element sub-chunks.
-//   wrow[r]  : row r of the unit in shared memory (uint4 index 0 = first element of the range contracted)
-//   xs8      : xs row of the unit's first sequence (float index 0 = same element), XSTR floats between sequences
-// acc[r][s] = (a0, a1): even / odd element chains exactly as row_dot() of the single-sequence kernel.
-template <int XSTR>
-__device__ __forceinline__ void unit_fma(const uint4* const (&wrow)[4], const float* xs8, int nsub, int lane,
-                                         float2 (&acc)[4][8]) {
-    const int sw = ((lane >> 2) & 1) * 4;
-#pragma unroll 1
-    for (int c = 0; c < nsub; ++c) {
-        float2 wp[4][4];
+// One 16-row weight tile x NB sequences over `nks` k-steps (16 elements each).
+//   arow  : shared-memory address of THIS LANE's A row (row lane & 15 of the tile), first byte of the row
+//   akey  : swizzle key of that row (global row index & 7);  ac0: first 16-byte chunk of the k-range inside the row
+//   xp    : shared-memory address of activation plane 0, sequence 0;  planes PSTR bytes apart, sequences H * 2 bytes apart,
+//           chunks swizzled by (sequence & 7);  xc0: first chunk of the k-range inside the activation row
+// acc[nt] = the m16n8 accumulator fragment of sequences 8 nt .. 8 nt + 7
+template <int H, int NT, int PSTR>
+__device__ __forceinline__ void mma_tile(uint32_t arow, int akey, int ac0, uint32_t xp, int xc0, int nks, int lane, float (&acc)[NT][4]) {
+    const int ahalf = lane >> 4;                         // A: lanes 16-31 address the k 8..15 halves
+    const int bpl = lane >> 4, bhalf = (lane >> 3) & 1, bseq = lane & 7;   // B x4: planes 0 / 1 by half-warp
+#pragma unroll 2
+    for (int ks = 0; ks < nks; ++ks) {
+        uint32_t a0, a1, a2, a3;
+        ldsm_x4(arow + (uint32_t)swz16(ac0 + 2 * ks + ahalf, akey) * 16u, a0, a1, a2, a3);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const uint4 w = wrow[r][c * 32 + lane];
-            wp[r][0] = make_float2(bf16_lo(w.x), bf16_hi(w.x)); wp[r][1] = make_float2(bf16_lo(w.y), bf16_hi(w.y));
-            wp[r][2] = make_float2(bf16_lo(w.z), bf16_hi(w.z)); wp[r][3] = make_float2(bf16_lo(w.w), bf16_hi(w.w));
-        }
-        const float* xc = xs8 + (c * 32 + lane) * 8;
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            const float4 xa = *reinterpret_cast<const float4*>(xc + s * XSTR + sw);
-            const float4 xb = *reinterpret_cast<const float4*>(xc + s * XSTR + 4 - sw);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                acc[r][s] = ffma2(wp[r][0], make_float2(xa.x, xa.y), acc[r][s]);
-                acc[r][s] = ffma2(wp[r][1], make_float2(xa.z, xa.w), acc[r][s]);
-                acc[r][s] = ffma2(wp[r][2], make_float2(xb.x, xb.y), acc[r][s]);
-                acc[r][s] = ffma2(wp[r][3], make_float2(xb.z, xb.w), acc[r][s]);
-            }
+        for (int nt = 0; nt < NT; ++nt) {
+            const int sq = nt * 8 + bseq;
+            const uint32_t xrow = xp + (uint32_t)sq * (H * 2) + (uint32_t)swz16(xc0 + 2 * ks + bhalf, sq & 7) * 16u;
+            uint32_t b00, b01, b10, b11, b20, b21;
+            ldsm_x4(xrow + (uint32_t)bpl * PSTR, b00, b01, b10, b11);
+            ldsm_x2(xrow + 2u * PSTR, b20, b21);         // (lanes 16-31 pass valid addresses that are ignored)
+            mma16816(acc[nt], a0, a1, a2, a3, b00, b01);
+            mma16816(acc[nt], a0, a1, a2, a3, b10, b11);
+            mma16816(acc[nt], a0, a1, a2, a3, b20, b21);
         }
     }
 }
-// lane L <- total of (row L >> 3, sequence L & 7)
-__device__ __forceinline__ float unit_reduce(float2 (&acc)[4][8], int lane) {
-    float v[32];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int s = 0; s < 8; ++s) v[r * 8 + s] = acc[r][s].x + acc[r][s].y;
-    return transpose_reduce32(v, lane);
+
+// ---- self-validating 4-byte exchange words (the all-to-all vectors: x after o_proj / down_proj, attention output,
+// SwiGLU activations).  A word is the fp32 value itself; 0xFFFFFFFF (a NaN pattern no result is ever published with)
+// means "not written yet".  Publication = one fire-and-forget red.and (performed at L2 at once, like red.max of the
+// tagged words); the gather polls 16-byte quads until none of the 4 words is the sentinel -- half the L2 traffic of
+// {value, tag} words, and that traffic (148 CTAs x every vector x NB sequences) is what bounds the batched step.
+// Every (layer, vector) has its own region, and there are two such sets: step s uses set s & 1 and, at its start,
+// re-arms (stores the sentinel into) the words THIS CTA wrote into the other set during step s - 1.  The kernel
+// boundary orders that re-arm before any publication of step s + 1 into it, so a poll can only ever see the sentinel or
+// the current step's value.
+static constexpr uint32_t SX_EMPTY = 0xFFFFFFFFu;
+__device__ __forceinline__ void sx_store(uint32_t* p, float v) {
+    uint32_t b = __float_as_uint(v);
+    if (b == SX_EMPTY) b = 0x7FFFFFFFu;                   // (another NaN)
+    asm volatile("red.relaxed.gpu.global.and.b32 [%0], %1;" ::"l"(p), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint4 sx_load4(const uint32_t* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
 }
 
 // per-head RMSNorm + RoPE of one 128-vector by one warp (lane holds d = lane, +32, +64, +96); input = tagged words
@@ -179,28 +185,32 @@ struct WCursor {
 };
 
 template <int H, int QD, int I, int NB, int NS, int KVK>
-__global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params p) {
+__global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params p) {   // 9 warps are allocated as 12 (granularity 4): 168 registers
     static_assert(NB % 8 == 0 && NB <= 16, "NB must be 8 or 16");
     static_assert(H % 256 == 0 && QD % H == 0 && I % H == 0, "chunking needs QD, I multiples of H, H multiple of 256");
-    constexpr int NSG = NB / 8;                 // sequence groups of 8
-    constexpr int XSTR = H;                     // floats between the xs rows of consecutive sequences
+    constexpr int NT = NB / 8;                  // m16n8 accumulator tiles per 16-row weight tile
+    constexpr int PSTR = NB * H * 2;            // bytes between the bf16 activation planes
+    constexpr int KSW = (H / 16) / NCONS_WARPS; // k-steps (of 16) each warp contracts per H-long chunk
+    static_assert(KSW >= 1, "H too small for an 8-way K split");
     constexpr int KPW = KVK / NCONS_WARPS;      // keys per warp in an attention tile
     constexpr int NV = 2 * KPW;                 // scores per lane before the butterfly (keys x 2 heads)
     constexpr int KV_TILE = KVK * HD * 4;
     constexpr int GROUP = 2;                    // q heads per kv head (checked on the host)
+    constexpr int XS_FLOATS = (3 * PSTR / 4 > ATT_SCRATCH) ? 3 * PSTR / 4 : ATT_SCRATCH;   // activation planes; attention scratch aliases them
     extern __shared__ __align__(128) uint8_t smem[];
     Ring ring;
     ring.slots = smem; ring.nslot = NS;
     uint8_t* kv_smem = smem + (size_t)NS * SLOT_BYTES;                 // [K tile | V tile]
-    float* xs = reinterpret_cast<float*>(kv_smem + 2 * KV_TILE);       // [NB][XSTR]
-    float* xres = xs + NB * XSTR;                                       // [NB][MAXROWS]
+    float* xs = reinterpret_cast<float*>(kv_smem + 2 * KV_TILE);       // bf16 planes [3][NB][H] (chunks swizzled by sequence)
+    float4* pbuf = reinterpret_cast<float4*>(xs + XS_FLOATS);           // [2][8 warps][NT][32 lanes] partial accumulator fragments
+    float* xres = reinterpret_cast<float*>(pbuf + 2 * NCONS_WARPS * NT * 32);   // [NB][MAXROWS]
     float* ropes = xres + NB * MAXROWS;                                 // [NB][128]  cos | sin of each sequence's position
     float* redk = ropes + NB * 128;                                     // [8 warps][32] K-split partials / scratch
     float* ssred = redk + NCONS_WARPS * 32;                             // [8 warps][NB] sums of squares
     float* rs = ssred + NCONS_WARPS * NB;                               // [NB] RMSNorm scales
-    float* bestv = rs + NB;                                             // [8 warps][NB]
-    int* besti = reinterpret_cast<int*>(bestv + NCONS_WARPS * NB);      // [8 warps][NB]
-    int* seqi = besti + NCONS_WARPS * NB;                               // pos[NB] | nact[NB] | off[NB + 1] | misc[4]
+    float* bestv = rs + NB;                                             // [16 rows][NB]
+    int* besti = reinterpret_cast<int*>(bestv + 16 * NB);               // [16 rows][NB]
+    int* seqi = besti + 16 * NB;                               // pos[NB] | nact[NB] | off[NB + 1] | misc[4]
     DecLayerW* ltab = reinterpret_cast<DecLayerW*>(seqi + 3 * NB + 8);  // [MAX_LAYERS]
     uint64_t* bars = reinterpret_cast<uint64_t*>(ltab + MAX_LAYERS);
     ring.full = bars; ring.empty = bars + NSLOT_MAX;
@@ -248,13 +258,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
         g = r / na; sp = r - g * na;
     };
 
+    // contiguous item range of this CTA and the owner of an item
+    const int it0 = (int)(((long long)blockIdx.x * T) / (int)G), it1 = (int)(((long long)(blockIdx.x + 1) * T) / (int)G);
+    auto item_owner = [&](int t) { return (int)((((long long)t + 1) * (int)G + T - 1) / T) - 1; };
+    auto range_start = [&](int c) { return (int)(((long long)c * T) / (int)G); };
+
     if (is_producer) {
         if (lane == 0) {
             WCursor<H, QD, I> wc;
             wc.init(p, ltab);
             uint32_t q = 0, kq = 0;
-            int kl = 0, kt = (int)blockIdx.x;     // K/V stream: (layer, item); item uses: 2 * i (K), 2 * i + 1 (V)
-            bool kv_done = (kt >= T);
+            int kl = 0, kt = it0;                 // K/V stream: (layer, item); item uses: 2 * i (K), 2 * i + 1 (V)
+            bool kv_done = (it0 >= it1);
             int kb = 0, kg = 0, ksp = 0;
             if (!kv_done) item_decode(kt, kb, kg, ksp);
             while (!wc.done || !kv_done) {
@@ -279,9 +294,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
                         mbar_expect_tx(&kv_full[st], bytes);
                         bulk_g2s(kv_smem + (size_t)st * KV_TILE, (st == 0 ? p.kcache : p.vcache) + off, bytes, &kv_full[st]);
                         ++kq; prog = true;
+                        if (st == 0 && kt == it0 && kl + 1 < p.L) {
+                            // The K/V stage only holds one tile each, and the attention phase alternates with the weight
+                            // phases: start pulling the NEXT layer's tiles of this CTA into L2 now, so that they stream from
+                            // HBM while the GEMV phases run and the stage refills from L2 when attention comes around again.
+                            for (int t = it0; t < it1; ++t) {
+                                int pb_, pg_, ps_;
+                                item_decode(t, pb_, pg_, ps_);
+                                const int n_ = min(KVK, pos_s[pb_] - ps_ * KVK);
+                                const size_t o_ = (size_t)(kl + 1) * p.cache_layer_stride + (size_t)pb_ * p.cache_seq_stride +
+                                                  ((size_t)pg_ * p.max_ctx + (size_t)ps_ * KVK) * HD;
+                                l2_prefetch(p.kcache + o_, (uint32_t)n_ * HD * 4);
+                                l2_prefetch(p.vcache + o_, (uint32_t)n_ * HD * 4);
+                            }
+                        }
                         if (st == 1) {          // V issued: next item
-                            kt += (int)G;
-                            if (kt >= T) { kt = (int)blockIdx.x; if (++kl >= p.L) kv_done = true; }
+                            if (++kt >= it1) { kt = it0; if (++kl >= p.L) kv_done = true; }
                             if (!kv_done) item_decode(kt, kb, kg, ksp);
                         }
                     }
@@ -293,6 +321,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
     }
 
     // ------------------------------ consumers ------------------------------
+    long long* dbg_row = nullptr; int dbg_i = 0;
+    if (p.dbg && (blockIdx.x == 0 || blockIdx.x == G - 1)) dbg_row = p.dbg + (blockIdx.x == 0 ? 0 : DBG_SLOTS);
+#define MARK() do { if (dbg_row && tid == 0 && dbg_i < DBG_SLOTS) dbg_row[dbg_i++] = clock64(); } while (0)
+    MARK();
     uint32_t q = 0, kq = 0;
     const unsigned epoch = __ldcg(p.bar + 1);
     const uint32_t tag_base = (epoch & 0xffffffu) << 8;
@@ -304,62 +336,93 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
         const int b = i / xrows, r = i - b * xrows;
         xres[b * MAXROWS + r] = __ldcg(p.x + (size_t)b * H + xsl.r0 + r);
     }
-    float best_v[NSG]; int best_i[NSG];
-#pragma unroll
-    for (int g = 0; g < NSG; ++g) { best_v[g] = -INFINITY; best_i[g] = 0x7fffffff; }
+    float best_v = -INFINITY; int best_i = 0x7fffffff;      // lm_head: running argmax of (tile row tid / NB, sequence tid % NB)
+    // exchange regions of this step (set = epoch parity) and re-arm of the other set (words this CTA wrote last step)
+    constexpr size_t SX_LAYER = (size_t)NB * (2 * H + QD + I);            // words per (set, layer): XO | XD | ATTN | ACT, each [seq][row]
+    uint32_t* const sx_cur = p.sx + (size_t)(epoch & 1u) * p.L * SX_LAYER;
+    {
+        uint32_t* const other = p.sx + (size_t)((epoch & 1u) ^ 1u) * p.L * SX_LAYER;
+        const Slice sa = make_slice(nullptr, I, H, 1);                    // act rows of this CTA = gate/up units
+        const Slice sq = make_slice(nullptr, QD, H, 1);                   // (attention outputs are re-armed by row range too)
+        for (int l = 0; l < p.L; ++l) {
+            uint32_t* base = other + (size_t)l * SX_LAYER;
+            for (int i = tid; i < NB * xrows; i += NCONS) {
+                const int b = i / xrows, r = i - b * xrows;
+                base[(size_t)b * H + xsl.r0 + r] = SX_EMPTY;                              // XO
+                base[(size_t)NB * H + (size_t)b * H + xsl.r0 + r] = SX_EMPTY;             // XD
+            }
+            const int ar = sa.r1 - sa.r0;
+            for (int i = tid; i < NB * ar; i += NCONS) {
+                const int b = i / ar, r = i - b * ar;
+                base[(size_t)NB * (2 * H + QD) + (size_t)b * I + sa.r0 + r] = SX_EMPTY;   // ACT
+            }
+            const int qr = sq.r1 - sq.r0;
+            for (int i = tid; i < NB * qr; i += NCONS) {
+                const int b = i / qr, r = i - b * qr;
+                base[(size_t)NB * 2 * H + (size_t)b * QD + sq.r0 + r] = SX_EMPTY;         // ATTN
+            }
+        }
+    }
 
-    // ---- gather of one H-long chunk of every active sequence into xs (raw values), optional RMSNorm ----
-    // src: tagged words, sequence b at src + b * src_stride; NORM: xs <- (x * r_b) * w  (rounding order of layers.rs:48-54)
-    constexpr int PP = (H / 2 + NCONS - 1) / NCONS;     // word pairs per thread and sequence
-    constexpr int SB = 8 / PP > 0 ? 8 / PP : 1;         // sequences per polling round (8 loads in flight per thread)
-    auto gather = [&](const uint2* src, size_t src_stride, uint32_t tag, const float* normw) {
-        float2 wv[PP];
+    // ---- gather of one H-long chunk of every active sequence into the activation planes, optional RMSNorm ----
+    // src: self-validating words, sequence b at src + b * src_stride.  Values stay in registers between the poll and
+    // the plane stores; NORM: x <- (x * r_b) * w  (rounding order of layers.rs:48-54), then the exact 3-way bf16 split.
+    const uint32_t xp_addr = smem_u32(xs);
+    auto store_planes = [&](int b, int j, float4 f) {       // quad j (elements 4 j .. 4 j + 3) of sequence b
+        const Split3 s0 = split3(f.x), s1 = split3(f.y), s2 = split3(f.z), s3 = split3(f.w);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(xs) + (size_t)b * (H * 2) + swz16(j >> 1, b & 7) * 16 + (j & 1) * 8;
+        auto pk = [](bf16 lo, bf16 hi) { return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16); };
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pk(s0.hi, s1.hi), pk(s2.hi, s3.hi));
+        *reinterpret_cast<uint2*>(dst + PSTR) = make_uint2(pk(s0.mid, s1.mid), pk(s2.mid, s3.mid));
+        *reinterpret_cast<uint2*>(dst + 2 * PSTR) = make_uint2(pk(s0.lo, s1.lo), pk(s2.lo, s3.lo));
+    };
+    constexpr int PP = (H / 4 + NCONS - 1) / NCONS;     // 16-byte quads per thread and sequence
+    static_assert(NB * PP <= 16, "gather keeps NB * PP quads per thread in registers");
+    // from_sx: poll self-validating words; else plain fp32 rows (layer 0: embeddings written by the previous step / prefill)
+    auto gather = [&](const uint32_t* src, size_t src_stride, const float* normw, bool from_sx) {
+        float4 wv[PP];
         if (normw) {
 #pragma unroll
             for (int i = 0; i < PP; ++i) {
                 const int j = tid + i * NCONS;
-                wv[i] = (j < H / 2) ? __ldg(reinterpret_cast<const float2*>(normw + xs_swz(2 * j))) : make_float2(0.f, 0.f);
+                wv[i] = (j < H / 4) ? __ldg(reinterpret_cast<const float4*>(normw + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        float ss[NB];
+        uint4 v[NB][PP];
+        bool ok;
+        do {      // loads are unconditional (idle slots re-poll the last active sequence / quad 0): registers only
+            ok = true;
 #pragma unroll
-        for (int b = 0; b < NB; ++b) ss[b] = 0.f;
+            for (int b = 0; b < NB; ++b)
 #pragma unroll
-        for (int b0 = 0; b0 < NB; b0 += SB) {
-            if (b0 < nb) {
-                uint4 v[SB][PP];
-                bool ok;
-                do {      // loads are unconditional (idle slots re-poll the last active sequence / word pair 0): registers only
-                    ok = true;
+                for (int i = 0; i < PP; ++i) {
+                    const int j = tid + i * NCONS;
+                    const int bb = min(b, nb - 1), jj = (PP * NCONS > H / 4 && j >= H / 4) ? 0 : j;
+                    v[b][i] = sx_load4(src + (size_t)bb * src_stride + 4 * jj);
+                }
+            if (from_sx) {
 #pragma unroll
-                    for (int sb = 0; sb < SB; ++sb)
+                for (int b = 0; b < NB; ++b)
 #pragma unroll
-                        for (int i = 0; i < PP; ++i) {
-                            const int j = tid + i * NCONS;
-                            const int bb = min(b0 + sb, nb - 1), jj = (PP * NCONS > H / 2 && j >= H / 2) ? 0 : j;
-                            v[sb][i] = ll_load2(src + (size_t)bb * src_stride + 2 * jj);
-                        }
-#pragma unroll
-                    for (int sb = 0; sb < SB; ++sb)
-#pragma unroll
-                        for (int i = 0; i < PP; ++i) ok = ok && (v[sb][i].y == tag) && (v[sb][i].w == tag);
-                } while (!ok);
-#pragma unroll
-                for (int sb = 0; sb < SB; ++sb)
-#pragma unroll
-                    for (int i = 0; i < PP; ++i) {
-                        const int j = tid + i * NCONS;
-                        if (b0 + sb < nb && j < H / 2) {
-                            const float a = __uint_as_float(v[sb][i].x), c = __uint_as_float(v[sb][i].z);
-                            *reinterpret_cast<float2*>(xs + (b0 + sb) * XSTR + xs_swz(2 * j)) = make_float2(a, c);
-                            ss[b0 + sb] = fmaf(a, a, ss[b0 + sb]); ss[b0 + sb] = fmaf(c, c, ss[b0 + sb]);
-                        }
-                    }
+                    for (int i = 0; i < PP; ++i)
+                        ok = ok && (v[b][i].x != SX_EMPTY) && (v[b][i].y != SX_EMPTY) && (v[b][i].z != SX_EMPTY) && (v[b][i].w != SX_EMPTY);
             }
-        }
+        } while (!ok);
         if (normw) {
 #pragma unroll
-            for (int b = 0; b < NB; ++b) { const float t = warp_sum(ss[b]); if (lane == 0) ssred[warp * NB + b] = t; }
+            for (int b = 0; b < NB; ++b) {
+                float t = 0.f;
+#pragma unroll
+                for (int i = 0; i < PP; ++i) {
+                    const int j = tid + i * NCONS;
+                    if (j < H / 4) {
+                        const float x0 = __uint_as_float(v[b][i].x), x1 = __uint_as_float(v[b][i].y), x2 = __uint_as_float(v[b][i].z), x3 = __uint_as_float(v[b][i].w);
+                        t = fmaf(x0, x0, t); t = fmaf(x1, x1, t); t = fmaf(x2, x2, t); t = fmaf(x3, x3, t);
+                    }
+                }
+                t = warp_sum(t);
+                if (lane == 0) ssred[warp * NB + b] = t;
+            }
             cons_sync();
             if (tid < nb) {
                 float tot = 0.f;
@@ -368,154 +431,141 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
                 rs[tid] = 1.0f / sqrtf(tot / H + p.eps);
             }
             cons_sync();
+        }
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                if (b < nb) {
-                    const float r = rs[b];
+        for (int b = 0; b < NB; ++b) {
+            if (b < nb) {
+                const float r = normw ? rs[b] : 1.f;
 #pragma unroll
-                    for (int i = 0; i < PP; ++i) {
-                        const int j = tid + i * NCONS;
-                        if (j < H / 2) {
-                            float2* px = reinterpret_cast<float2*>(xs + b * XSTR + xs_swz(2 * j));
-                            const float2 xv = *px;
-                            *px = make_float2((xv.x * r) * wv[i].x, (xv.y * r) * wv[i].y);
-                        }
+                for (int i = 0; i < PP; ++i) {
+                    const int j = tid + i * NCONS;
+                    if (j < H / 4) {
+                        float4 f = make_float4(__uint_as_float(v[b][i].x), __uint_as_float(v[b][i].y), __uint_as_float(v[b][i].z), __uint_as_float(v[b][i].w));
+                        if (normw) f = make_float4((f.x * r) * wv[i].x, (f.y * r) * wv[i].y, (f.z * r) * wv[i].z, (f.w * r) * wv[i].w);
+                        store_planes(b, j, f);
                     }
                 }
             }
         }
         cons_sync();
     };
-    // layer 0: the pending tokens' embeddings come from plain memory (written by the previous step / prefill)
-    auto load_x0 = [&](const float* normw) {
-        float ss[NB];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            ss[b] = 0.f;
-            if (b < nb)
-                for (int i = tid; i < H; i += NCONS) { const float v = __ldcg(p.x + (size_t)b * H + i); xs[b * XSTR + xs_swz(i)] = v; ss[b] = fmaf(v, v, ss[b]); }
-        }
-#pragma unroll
-        for (int b = 0; b < NB; ++b) { const float t = warp_sum(ss[b]); if (lane == 0) ssred[warp * NB + b] = t; }
-        cons_sync();
-        if (tid < nb) {
-            float tot = 0.f;
-#pragma unroll
-            for (int w8 = 0; w8 < NCONS_WARPS; ++w8) tot += ssred[w8 * NB + tid];
-            rs[tid] = 1.0f / sqrtf(tot / H + p.eps);
-        }
-        cons_sync();
-        for (int b = 0; b < nb; ++b) {
-            const float r = rs[b];
-            for (int i = tid; i < H; i += NCONS) { const int e = xs_swz(i); xs[b * XSTR + e] = (xs[b * XSTR + e] * r) * __ldg(normw + e); }
-        }
-        cons_sync();
-    };
 
-    // ---- K = H phases: rows stream through the ring, unit = (4 rows of a slot, 8 sequences) ----
-    auto rows_phase = [&](const Slice& s, int epi, uint2* out, size_t out_stride, uint32_t tag) {
-        int ubase = 0;
+    // sum of the 8 warps' partial accumulator fragments (fixed order) for element (tile row tid / NB, sequence tid % NB)
+    auto tile_sum = [&](int par) {
+        const int row = tid / NB, sq = tid - row * NB;
+        const int nt = sq >> 3, col = sq & 7;
+        const int ln = (row & 7) * 4 + (col >> 1), reg = (row >> 3) * 2 + (col & 1);
+        const float* pb = reinterpret_cast<const float*>(pbuf + (size_t)par * NCONS_WARPS * NT * 32) + ((size_t)nt * 32 + ln) * 4 + reg;
+        float t = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < NCONS_WARPS; ++w8) t += pb[(size_t)w8 * NT * 32 * 4];
+        return t;
+    };
+    int ppar = 0;      // partial-buffer parity (double buffer: a tile's sums are read while the next tile's partials are written)
+
+    // ---- K = H phases: rows stream through the ring; every 16-row tile is contracted by all 8 warps (K split 8 ways) ----
+    // BE_STORE publishes tagged words into `out` (q/k/v: read by the few attention CTAs of each head), BE_SWIGLU publishes
+    // self-validating words into `sxo` (activations: gathered by every CTA), BE_ARGMAX keeps the running argmax
+    auto rows_phase = [&](const Slice& s, int epi, uint2* out, size_t out_stride, uint32_t tag, uint32_t* sxo) {
         for (int r = s.r0; r < s.r1; r += s.rpc, ++q) {
             const int rows = min(s.rpc, s.r1 - r);
             const uint32_t slot = q % NS, par = (q / NS) & 1;
             mbar_wait(&ring.full[slot], par);
-            const uint4* base = reinterpret_cast<const uint4*>(ring.slots + (size_t)slot * SLOT_BYTES);
-            const int units = ((rows + 3) >> 2) * NSG;
-            for (int j = (warp - (ubase & 7) + 8) & 7; j < units; j += NCONS_WARPS) {
-                const int rg = j / NSG, sg = j - rg * NSG;
-                const uint4* wrow[4];
+            const uint32_t sbase = smem_u32(ring.slots + (size_t)slot * SLOT_BYTES);
+            for (int t0 = 0; t0 < rows; t0 += 16) {
+                const int ri = min(t0 + (lane & 15), rows - 1);          // rows past the slot's last row alias it (never published)
+                float acc[NT][4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) wrow[i] = base + (size_t)(rg * 4 + i) * (H / 8);
-                float2 acc[4][8];
+                for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int k = 0; k < 4; ++k) acc[nt][k] = 0.f;
+                mma_tile<H, NT, PSTR>(sbase + (uint32_t)ri * (H * 2), (r + ri) & 7, warp * KSW * 2, xp_addr, warp * KSW * 2, KSW, lane, acc);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) acc[i][k] = make_float2(0.f, 0.f);
-                unit_fma<XSTR>(wrow, xs + sg * 8 * XSTR, H / 256, lane, acc);
-                const float v = unit_reduce(acc, lane);
-                const int rr = rg * 4 + (lane >> 3), sq = sg * 8 + (lane & 7), row = r + rr;
-                const bool valid = rr < rows && sq < nb;
-                if (epi == BE_STORE) {
-                    if (valid) ll_store(out + (size_t)sq * out_stride + row, v, tag);
-                } else if (epi == BE_SWIGLU) {
-                    const float up = __shfl_xor_sync(0xffffffffu, v, 8);      // rows 2j (gate) and 2j + 1 (up) sit 8 lanes apart
-                    if (valid && !(rr & 1)) ll_store(out + (size_t)sq * out_stride + (row >> 1), silu(v) * up, tag);
-                } else {
-#pragma unroll
-                    for (int g = 0; g < NSG; ++g)
-                        if (valid && sg == g && (v > best_v[g] || (v == best_v[g] && row < best_i[g]))) { best_v[g] = v; best_i[g] = row; }
+                for (int nt = 0; nt < NT; ++nt)
+                    pbuf[((size_t)ppar * NCONS_WARPS + warp) * NT * 32 + nt * 32 + lane] = make_float4(acc[nt][0], acc[nt][1], acc[nt][2], acc[nt][3]);
+                if (t0 + 16 >= rows) {                                   // last tile of the slot: this warp is done with its weights
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ring.empty[slot]);
                 }
+                cons_sync();
+                if (tid < 16 * NB) {
+                    const float v = tile_sum(ppar);
+                    const int rr = t0 + tid / NB, sq = tid % NB, row = r + rr;
+                    const bool valid = rr < rows && sq < nb;
+                    if (epi == BE_STORE) {
+                        if (valid) ll_store(out + (size_t)sq * out_stride + row, v, tag);
+                    } else if (epi == BE_SWIGLU) {
+                        const float up = __shfl_down_sync(0xffffffffu, v, NB);     // rows 2j (gate) and 2j + 1 (up): NB threads apart
+                        if (valid && !(rr & 1)) sx_store(sxo + (size_t)sq * I + (row >> 1), silu(v) * up);
+                    } else {
+                        if (valid && (v > best_v || (v == best_v && row < best_i))) { best_v = v; best_i = row; }
+                    }
+                }
+                ppar ^= 1;
             }
-            ubase += units;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ring.empty[slot]);
         }
     };
 
-    // ---- K = NCH * H phases with <= 8 resident rows (o_proj, down_proj): x walks through xs in H-long chunks,
-    //      units = (4 rows, 8 sequences, 1 / KP of every chunk); partials combine through shared memory;
-    //      result: residual add + publication (layers.rs:454,460) ----
-    auto resident_phase = [&](const Slice& s, int NCH, const uint2* src, size_t src_stride, uint32_t src_tag, uint32_t tag) {
+    // ---- K = NCH * H phases with <= 8 resident rows (o_proj, down_proj): the activation planes hold one H-long chunk at
+    //      a time, every chunk is contracted by all 8 warps into the same accumulators; result: residual add +
+    //      publication into `sxo` (layers.rs:454,460) ----
+    auto resident_phase = [&](const Slice& s, int NCH, const uint32_t* src, size_t src_stride, uint32_t* sxo) {
         const int rows = s.r1 - s.r0;
         const int nslots = (rows + s.rpc - 1) / s.rpc;
-        const int nrg = (rows + 3) >> 2;
-        int KP = 8 / (nrg * NSG); if (KP > H / 256) KP = H / 256; if (KP > 4) KP = 4;
-        const int u = warp / KP, kp = warp - u * KP;
-        const bool active = u < nrg * NSG;
-        const int rg = u / NSG, sg = u - rg * NSG;
-        const uint8_t* rowp[4];
+        const int ri = min(lane & 15, rows - 1);                          // rows past the slice alias the last row (never published)
+        const uint32_t arow = smem_u32(ring.slots + (size_t)((q + ri / s.rpc) % NS) * SLOT_BYTES) + (uint32_t)(ri % s.rpc) * (uint32_t)(s.K * 2);
+        float acc[NT][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int ri = min(rg * 4 + i, rows - 1);                     // rows past the slice alias the last row (never published)
-            const uint32_t slot = (q + ri / s.rpc) % NS;
-            rowp[i] = ring.slots + (size_t)slot * SLOT_BYTES + (size_t)(ri % s.rpc) * s.K * 2;
-        }
-        float2 acc[4][8];
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[i][k] = make_float2(0.f, 0.f);
-        const int nsub = (H / 256) / KP;
+            for (int k = 0; k < 4; ++k) acc[nt][k] = 0.f;
         for (int ch = 0; ch < NCH; ++ch) {
-            gather(src + (size_t)ch * H, src_stride, src_tag, nullptr);
+            gather(src + (size_t)ch * H, src_stride, nullptr, true);
             if (ch == 0)
                 for (int i = 0; i < nslots; ++i) mbar_wait(&ring.full[(q + i) % NS], ((q + i) / NS) & 1);
-            if (active) {
-                const uint4* wrow[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) wrow[i] = reinterpret_cast<const uint4*>(rowp[i] + ((size_t)ch * H + (size_t)kp * nsub * 256) * 2);
-                unit_fma<XSTR>(wrow, xs + sg * 8 * XSTR + kp * nsub * 256, nsub, lane, acc);
-            }
-            cons_sync();                                                  // xs may be overwritten by the next chunk
+            mma_tile<H, NT, PSTR>(arow, (s.r0 + ri) & 7, ch * (H / 8) + warp * KSW * 2, xp_addr, warp * KSW * 2, KSW, lane, acc);
+            cons_sync();                                                  // the planes may be overwritten by the next chunk
         }
         __syncwarp();
         if (lane == 0) for (int i = 0; i < nslots; ++i) mbar_arrive(&ring.empty[(q + i) % NS]);
         q += nslots;
-        const float v = unit_reduce(acc, lane);
-        redk[warp * 32 + lane] = v;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+            pbuf[((size_t)ppar * NCONS_WARPS + warp) * NT * 32 + nt * 32 + lane] = make_float4(acc[nt][0], acc[nt][1], acc[nt][2], acc[nt][3]);
         cons_sync();
-        if (active && kp == 0) {
-            float tot = v;
-            for (int k = 1; k < KP; ++k) tot += redk[(warp + k) * 32 + lane];
-            const int rr = rg * 4 + (lane >> 3), sq = sg * 8 + (lane & 7);
+        if (tid < 16 * NB) {
+            const float tot = tile_sum(ppar);
+            const int rr = tid / NB, sq = tid % NB;
             if (rr < rows && sq < nb) {
                 const float nv = xres[sq * MAXROWS + rr] + tot;
                 xres[sq * MAXROWS + rr] = nv;
-                ll_store(p.x_ll + (size_t)sq * H + s.r0 + rr, nv, tag);
+                sx_store(sxo + (size_t)sq * H + s.r0 + rr, nv);
             }
         }
+        ppar ^= 1;
     };
 
     for (int l = 0; l < p.L; ++l) {
         const DecLayerW w = ltab[l];
         const uint32_t tl = tag_base | ((uint32_t)l << 3);
+        uint32_t* const sxl = sx_cur + (size_t)l * SX_LAYER;                       // this layer's XO | XD | ATTN | ACT words
+        uint32_t* const sx_xo = sxl; uint32_t* const sx_xd = sxl + (size_t)NB * H;
+        uint32_t* const sx_attn = sxl + (size_t)NB * 2 * H; uint32_t* const sx_act = sxl + (size_t)NB * (2 * H + QD);
         // ---- phase 1: RMSNorm + [q|k|v] GEMV ----
-        if (l == 0) load_x0(w.ln_in);
-        else gather(p.x_ll, H, (tag_base | ((uint32_t)(l - 1) << 3)) | PH_XD, w.ln_in);
+        if (l == 0) gather(reinterpret_cast<const uint32_t*>(p.x), H, w.ln_in, false);
+        else gather(sxl - SX_LAYER + (size_t)NB * H, H, w.ln_in, true);            // XD of the previous layer
+        MARK();
         sl_qkv.W = w.wqkv;
-        rows_phase(sl_qkv, BE_STORE, p.qkv_ll, (size_t)(QD + 2 * p.KVD), tl | PH_QKV);
+        rows_phase(sl_qkv, BE_STORE, p.qkv_ll, (size_t)(QD + 2 * p.KVD), tl | PH_QKV, nullptr);
         cons_sync();                                  // xs is free: attention scratch aliases it
+        MARK();
         // ---- phase 2: attention partials of this CTA's work items ----
+        // Items are sorted (sequence, kv head, split) and dealt in CONTIGUOUS ranges: a CTA's range consists of a few
+        // "runs" of consecutive splits of one (sequence, kv head).  Within a run every warp keeps an online-softmax
+        // state (max, sum, 4 output dims per lane, both q heads) in registers over the tiles -- no CTA barrier per
+        // tile -- and the 8 warp states are merged through shared memory once per run: one partial record per
+        // (CTA, run), stored at the slot of the run's first split.  A run starts at split 0 and wherever a CTA's range
+        // starts, so the merging CTA can enumerate the slots that will be written.
         {
             float* qs = xs;                           // [2][128]
             float* kn = qs + GROUP * HD;              // [128]
@@ -525,10 +575,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
             float* snew = wml + NCONS_WARPS * 4;      // [2]
             float* Ks = reinterpret_cast<float*>(kv_smem);
             float* Vs = reinterpret_cast<float*>(kv_smem + KV_TILE);
-            for (int t = (int)blockIdx.x; t < T; t += (int)G) {
+            constexpr int SH = (NV == 16) ? 1 : (NV == 8 ? 2 : 3);
+            int t = it0;
+            while (t < it1) {
                 int b, g, sp;
                 item_decode(t, b, g, sp);
-                const int nloc = min(KVK, pos_s[b] - sp * KVK);
+                const int nrun = min(nact_s[b] - sp, it1 - t);
                 const float* cs = ropes + b * 128; const float* sn = cs + 64;
                 if (warp < GROUP)
                     head_norm_rope_b(p.qkv_ll + (size_t)b * (QD + 2 * p.KVD) + (size_t)(g * GROUP + warp) * HD, tl | PH_QKV,
@@ -536,61 +588,72 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
                 cons_sync();
                 const float4 q0 = *reinterpret_cast<const float4*>(qs + lane * 4);
                 const float4 q1 = *reinterpret_cast<const float4*>(qs + HD + lane * 4);
-                mbar_wait(&kv_full[0], (kq >> 1) & 1);
-                float pv[NV];
-#pragma unroll
-                for (int kk = 0; kk < KPW; ++kk) {
-                    const int j = warp + 8 * kk;      // rows past the split's last key hold stale data and are masked below
-                    const float4 kv = *reinterpret_cast<const float4*>(Ks + j * HD + lane * 4);
-                    pv[2 * kk] = fmaf(kv.x, q0.x, fmaf(kv.y, q0.y, fmaf(kv.z, q0.z, kv.w * q0.w)));
-                    pv[2 * kk + 1] = fmaf(kv.x, q1.x, fmaf(kv.y, q1.y, fmaf(kv.z, q1.z, kv.w * q1.w)));
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&kv_empty[0]);     // K stage may be refilled
-                // transposing butterfly: lane L ends with score index L >> SH (index = 2 * key + head)
-                constexpr int SH = (NV == 16) ? 1 : (NV == 8 ? 2 : 3);
-#pragma unroll
-                for (int o = 16, n = NV; n > 1; o >>= 1, n >>= 1) {
-                    const bool up = lane & o;
-#pragma unroll
-                    for (int i = 0; i < n / 2; ++i) {
-                        const float send = up ? pv[i] : pv[i + n / 2];
-                        const float keep = up ? pv[i + n / 2] : pv[i];
-                        pv[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-                    }
-                }
-#pragma unroll
-                for (int o = (1 << SH) >> 1; o > 0; o >>= 1) pv[0] += __shfl_xor_sync(0xffffffffu, pv[0], o);
-                const int sidx = lane >> SH;                                   // 2 * kk + head
-                const bool mine = warp + 8 * (sidx >> 1) < nloc;
-                const float sv = mine ? pv[0] / sqrtf((float)HD) : -INFINITY;
-                float mw = sv;                                                 // max over this warp's keys, per head
-#pragma unroll
-                for (int o = 2 << SH; o < 32; o <<= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
-                const float ev = mine ? expf(sv - mw) : 0.f;
-                float lw = ev;
-#pragma unroll
-                for (int o = 2 << SH; o < 32; o <<= 1) lw += __shfl_xor_sync(0xffffffffu, lw, o);
-                mbar_wait(&kv_full[1], (kq >> 1) & 1);
+                float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;       // running (max, sum) of head 0 / 1
                 float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+                for (int it = 0; it < nrun; ++it) {
+                    const int nloc = min(KVK, pos_s[b] - (sp + it) * KVK);
+                    mbar_wait(&kv_full[0], (kq >> 1) & 1);
+                    float pv[NV];
 #pragma unroll
-                for (int kk = 0; kk < KPW; ++kk) {
-                    const int j = warp + 8 * kk;
-                    const float4 vv = *reinterpret_cast<const float4*>(Vs + j * HD + lane * 4);
-                    const float e0 = __shfl_sync(0xffffffffu, ev, (2 * kk) << SH), e1 = __shfl_sync(0xffffffffu, ev, (2 * kk + 1) << SH);
-                    if (j < nloc) {       // (a stale V row may hold non-finite garbage: 0 * inf must not reach the sum)
-                        o0.x = fmaf(e0, vv.x, o0.x); o0.y = fmaf(e0, vv.y, o0.y); o0.z = fmaf(e0, vv.z, o0.z); o0.w = fmaf(e0, vv.w, o0.w);
-                        o1.x = fmaf(e1, vv.x, o1.x); o1.y = fmaf(e1, vv.y, o1.y); o1.z = fmaf(e1, vv.z, o1.z); o1.w = fmaf(e1, vv.w, o1.w);
+                    for (int kk = 0; kk < KPW; ++kk) {
+                        const int j = warp + 8 * kk;      // rows past the split's last key hold stale data and are masked below
+                        const float4 kv = *reinterpret_cast<const float4*>(Ks + j * HD + lane * 4);
+                        pv[2 * kk] = fmaf(kv.x, q0.x, fmaf(kv.y, q0.y, fmaf(kv.z, q0.z, kv.w * q0.w)));
+                        pv[2 * kk + 1] = fmaf(kv.x, q1.x, fmaf(kv.y, q1.y, fmaf(kv.z, q1.z, kv.w * q1.w)));
                     }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&kv_empty[0]);     // K stage may be refilled
+                    // transposing butterfly: lane L ends with score index L >> SH (index = 2 * key + head)
+#pragma unroll
+                    for (int o = 16, n = NV; n > 1; o >>= 1, n >>= 1) {
+                        const bool up = lane & o;
+#pragma unroll
+                        for (int i = 0; i < n / 2; ++i) {
+                            const float send = up ? pv[i] : pv[i + n / 2];
+                            const float keep = up ? pv[i + n / 2] : pv[i];
+                            pv[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                        }
+                    }
+#pragma unroll
+                    for (int o = (1 << SH) >> 1; o > 0; o >>= 1) pv[0] += __shfl_xor_sync(0xffffffffu, pv[0], o);
+                    const int sidx = lane >> SH;                                   // 2 * kk + head
+                    const bool mine = warp + 8 * (sidx >> 1) < nloc;
+                    const float sv = mine ? pv[0] / sqrtf((float)HD) : -INFINITY;
+                    float mw = sv;                                                 // max over this warp's keys of the tile, per head
+#pragma unroll
+                    for (int o = 2 << SH; o < 32; o <<= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+                    const float mwo = __shfl_xor_sync(0xffffffffu, mw, 1 << SH);  // the other head's
+                    const bool h1 = sidx & 1;
+                    const float n0 = fmaxf(m0, h1 ? mwo : mw), n1 = fmaxf(m1, h1 ? mw : mwo);     // new running maxima
+                    const float c0 = (m0 == -INFINITY) ? 0.f : expf(m0 - n0), c1 = (m1 == -INFINITY) ? 0.f : expf(m1 - n1);
+                    const float ev = mine ? expf(sv - (h1 ? n1 : n0)) : 0.f;
+                    float lw = ev;
+#pragma unroll
+                    for (int o = 2 << SH; o < 32; o <<= 1) lw += __shfl_xor_sync(0xffffffffu, lw, o);
+                    const float lwo = __shfl_xor_sync(0xffffffffu, lw, 1 << SH);
+                    l0 = fmaf(l0, c0, h1 ? lwo : lw); l1 = fmaf(l1, c1, h1 ? lw : lwo);
+                    m0 = n0; m1 = n1;
+                    o0.x *= c0; o0.y *= c0; o0.z *= c0; o0.w *= c0; o1.x *= c1; o1.y *= c1; o1.z *= c1; o1.w *= c1;
+                    mbar_wait(&kv_full[1], (kq >> 1) & 1);
+#pragma unroll
+                    for (int kk = 0; kk < KPW; ++kk) {
+                        const int j = warp + 8 * kk;
+                        const float4 vv = *reinterpret_cast<const float4*>(Vs + j * HD + lane * 4);
+                        const float e0 = __shfl_sync(0xffffffffu, ev, (2 * kk) << SH), e1 = __shfl_sync(0xffffffffu, ev, (2 * kk + 1) << SH);
+                        if (j < nloc) {       // (a stale V row may hold non-finite garbage: 0 * inf must not reach the sum)
+                            o0.x = fmaf(e0, vv.x, o0.x); o0.y = fmaf(e0, vv.y, o0.y); o0.z = fmaf(e0, vv.z, o0.z); o0.w = fmaf(e0, vv.w, o0.w);
+                            o1.x = fmaf(e1, vv.x, o1.x); o1.y = fmaf(e1, vv.y, o1.y); o1.z = fmaf(e1, vv.z, o1.z); o1.w = fmaf(e1, vv.w, o1.w);
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&kv_empty[1]);     // V stage may be refilled
+                    kq += 2;
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&kv_empty[1]);     // V stage may be refilled
-                kq += 2;
                 *reinterpret_cast<float4*>(osum + (warp * 2 + 0) * HD + lane * 4) = o0;
                 *reinterpret_cast<float4*>(osum + (warp * 2 + 1) * HD + lane * 4) = o1;
-                if (lane == 0 || lane == (1 << SH)) { const int h = lane >> SH; wml[(warp * 2 + h) * 2] = mw; wml[(warp * 2 + h) * 2 + 1] = lw; }
+                if (lane == 0) { wml[(warp * 2 + 0) * 2] = m0; wml[(warp * 2 + 0) * 2 + 1] = l0; wml[(warp * 2 + 1) * 2] = m1; wml[(warp * 2 + 1) * 2 + 1] = l1; }
                 cons_sync();
                 {
                     const int hq = tid / HD, d = tid - hq * HD;      // NCONS == 2 * HD
@@ -604,17 +667,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
                         acc = fmaf(f, osum[(w8 * 2 + hq) * HD + d], acc);
                         Ls = fmaf(f, wml[(w8 * 2 + hq) * 2 + 1], Ls);
                     }
+                    // record slot = split index of the run's first tile
                     uint2* rec = p.part_ll + ((((size_t)b * p.nkv + g) * MAXSPLIT + sp) * GROUP + hq) * PSTRIDE;
                     ll_store(rec + d, acc, tl | PH_PART);
                     if (d < 2) ll_store(rec + HD + d, d == 0 ? M : Ls, tl | PH_PART);
                 }
-                cons_sync();                          // scratch may be overwritten by the next item
+                cons_sync();                          // scratch may be overwritten by the next run
+                t += nrun;
             }
-            // ---- merge of one (sequence, kv head): all its splits + the current token's key / value ----
+            MARK();
+            // ---- merge of one (sequence, kv head): all its partial records + the current token's key / value ----
             const int mid = (int)G - 1 - (int)blockIdx.x;
             if (mid < nb * p.nkv) {
                 const int b = mid / p.nkv, g = mid - b * p.nkv;
-                const int pos = pos_s[b], nact = nact_s[b];
+                const int pos = pos_s[b];
+                const int base_t = off_s[b] * p.nkv + g * nact_s[b];
+                const int nact = nact_s[b];                                                        // record slots of (b, g)
+                // slot u holds a record iff a run starts at split u: u == 0 or item base_t + u opens its owner's range
+                auto run_start = [&](int u) { return u == 0 || range_start(item_owner(base_t + u)) == base_t + u; };
+                unsigned startmask = 0;
+                for (int u = 0; u < nact; ++u) startmask |= run_start(u) ? (1u << u) : 0u;
                 const float* cs = ropes + b * 128; const float* sn = cs + 64;
                 const uint2* qkvb = p.qkv_ll + (size_t)b * (QD + 2 * p.KVD);
                 if (warp < GROUP) head_norm_rope_b(qkvb + (size_t)(g * GROUP + warp) * HD, tl | PH_QKV, w.qnorm, p.eps, cs, sn, qs + warp * HD, lane);
@@ -648,7 +720,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
                     auto load_round = [&](int u0) {
 #pragma unroll
                         for (int u = 0; u < RB; ++u)
-                            if (u0 + u < nact) {
+                            if (u0 + u < nact && ((startmask >> (u0 + u)) & 1u)) {
                                 const uint2* rec = recb + (size_t)(u0 + u) * GROUP * PSTRIDE;
                                 asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(ov[u].x), "=r"(ov[u].y) : "l"(rec + d) : "memory");
                             }
@@ -656,12 +728,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
                     auto round_ok = [&](int u0) {
                         bool k = true;
 #pragma unroll
-                        for (int u = 0; u < RB; ++u) if (u0 + u < nact) k = k && (ov[u].y == tg);
+                        for (int u = 0; u < RB; ++u) if (u0 + u < nact && ((startmask >> (u0 + u)) & 1u)) k = k && (ov[u].y == tg);
                         return k;
                     };
-                    do {        // first round: (max, sum) of every split (one per lane) + the first RB partial outputs
+                    const bool has_rec = lane < nact && ((startmask >> lane) & 1u);
+                    do {        // first round: (max, sum) of every record (one per lane) + the first RB partial outputs
                         mv.y = tg; lv.y = tg; mv.x = 0u; lv.x = 0u;
-                        if (lane < nact) {
+                        if (has_rec) {
                             const uint2* rec = recb + (size_t)lane * GROUP * PSTRIDE;
                             asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(mv.x), "=r"(mv.y) : "l"(rec + HD) : "memory");
                             asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(lv.x), "=r"(lv.y) : "l"(rec + HD + 1) : "memory");
@@ -669,10 +742,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
                         load_round(0);
                         ok = __all_sync(0xffffffffu, (mv.y == tg) && (lv.y == tg) && round_ok(0));
                     } while (!ok);
-                    // softmax merge, one partial per lane: lanes < nact hold a split; the current token's key is one more
-                    // partial (max = its score, sum = 1, output = its value row) handled outside the lane array
-                    const float m_l = lane < nact ? __uint_as_float(mv.x) : -INFINITY;
-                    const float l_l = lane < nact ? __uint_as_float(lv.x) : 0.f;
+                    // softmax merge, one record per lane; the current token's key is one more partial (max = its score,
+                    // sum = 1, output = its value row)
+                    const float m_l = has_rec ? __uint_as_float(mv.x) : -INFINITY;
+                    const float l_l = has_rec ? __uint_as_float(lv.x) : 0.f;
                     const float sn_ = snew[hq];
                     const float M = fmaxf(warp_max(m_l), sn_);
                     const float f = expf(m_l - M);                       // exp(-inf) = 0 on idle lanes
@@ -683,43 +756,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
                         if (u0 > 0) { do { load_round(u0); ok = __all_sync(0xffffffffu, round_ok(u0)); } while (!ok); }
 #pragma unroll
                         for (int u = 0; u < RB; ++u)
-                            if (u0 + u < nact) O = fmaf(__shfl_sync(0xffffffffu, f, u0 + u), __uint_as_float(ov[u].x), O);
+                            if (u0 + u < nact && ((startmask >> (u0 + u)) & 1u)) O = fmaf(__shfl_sync(0xffffffffu, f, u0 + u), __uint_as_float(ov[u].x), O);
                     }
-                    ll_store(p.attn_ll + (size_t)b * QD + (size_t)(g * GROUP + hq) * HD + d, O / Lsum, tl | PH_ATTN);
+                    sx_store(sx_attn + (size_t)b * QD + (size_t)(g * GROUP + hq) * HD + d, O / Lsum);
                 }
                 cons_sync();                          // attention scratch (aliases xs) is free again
             }
         }
+        MARK();
         // ---- phase 3: o_proj GEMV + residual ----
         sl_o.W = w.wo;
-        resident_phase(sl_o, QD / H, p.attn_ll, QD, tl | PH_ATTN, tl | PH_XO);
+        resident_phase(sl_o, QD / H, sx_attn, QD, sx_xo);
+        MARK();
         // ---- phase 4: RMSNorm + gate/up GEMV + SiLU*mul ----
-        gather(p.x_ll, H, tl | PH_XO, w.ln_post);
+        gather(sx_xo, H, w.ln_post, true);
+        MARK();
         sl_gu.W = w.wgu;
-        rows_phase(sl_gu, BE_SWIGLU, p.act_ll, (size_t)I, tl | PH_ACT);
+        rows_phase(sl_gu, BE_SWIGLU, nullptr, 0, 0u, sx_act);
         cons_sync();
+        MARK();
         // ---- phase 5: down GEMV + residual ----
         sl_dn.W = w.wdown;
-        resident_phase(sl_dn, I / H, p.act_ll, I, tl | PH_ACT, tl | PH_XD);
+        resident_phase(sl_dn, I / H, sx_act, I, sx_xd);
+        MARK();
     }
     // ---- final RMSNorm + tied lm_head GEMV + argmax ----
-    gather(p.x_ll, H, (tag_base | ((uint32_t)(p.L - 1) << 3)) | PH_XD, p.final_norm);
-    rows_phase(make_slice(p.lm_head, p.V, H, 1), BE_ARGMAX, nullptr, 0, 0u);
-    // candidates of sequence sq live in the 4 lanes sharing (lane & 7): merge over the row bits (lane bits 3, 4)
-#pragma unroll
-    for (int g = 0; g < NSG; ++g) {
-#pragma unroll
-        for (int o = 8; o <= 16; o <<= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best_v[g], o); const int oi = __shfl_xor_sync(0xffffffffu, best_i[g], o);
-            if (ov > best_v[g] || (ov == best_v[g] && oi < best_i[g])) { best_v[g] = ov; best_i[g] = oi; }
-        }
-        if (lane < 8) { bestv[warp * NB + g * 8 + lane] = best_v[g]; besti[warp * NB + g * 8 + lane] = best_i[g]; }
-    }
+    gather(sx_cur + (size_t)(p.L - 1) * SX_LAYER + (size_t)NB * H, H, p.final_norm, true);
+    MARK();
+    rows_phase(make_slice(p.lm_head, p.V, H, 1), BE_ARGMAX, nullptr, 0, 0u, nullptr);
+    MARK();
+    // every thread tid < 16 NB holds the best row of (tile row tid / NB, sequence tid % NB): merge the 16 tile rows per sequence
+    cons_sync();
+    if (tid < 16 * NB) { bestv[tid] = best_v; besti[tid] = best_i; }
     cons_sync();
     int& is_last = misc[0];
     if (tid < nb) {
         float v = -INFINITY; int idx = 0x7fffffff;
-        for (int wq = 0; wq < NCONS_WARPS; ++wq) {
+        for (int wq = 0; wq < 16; ++wq) {
             const float cv = bestv[wq * NB + tid]; const int ci = besti[wq * NB + tid];
             if (cv > v || (cv == v && ci < idx)) { v = cv; idx = ci; }
         }
@@ -771,16 +844,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
 }  // namespace megab
 
 // host side ---------------------------------------------------------------------------------------
+static long long* g_last_dbg_batch = nullptr;   // debug only (ASRB_MEGA_DEBUG): timeline buffer of the last batched launch
+int decode_batch_debug_timeline(long long* out, int cap) {
+    if (!g_last_dbg_batch || cap < 2 * mega::DBG_SLOTS) return 0;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, g_last_dbg_batch, 2 * mega::DBG_SLOTS * sizeof(long long), cudaMemcpyDeviceToHost);
+    return mega::DBG_SLOTS;
+}
+
 template <int H, int QD, int I> static bool bdims_match(const asrb_dims& c) {
     return c.hidden_size == H && c.num_attention_heads * c.head_dim == QD && c.intermediate_size == I;
 }
 struct BatchCfg { int NB, NS, KVK; };
-static BatchCfg batch_cfg(int B) { return B <= 8 ? BatchCfg{8, 3, 64} : BatchCfg{16, 3, 32}; }
+static BatchCfg batch_cfg(int B) { return B <= 8 ? BatchCfg{8, 3, 64} : BatchCfg{16, 2, 32}; }
 
 static size_t batch_smem_bytes(int H, const BatchCfg& k) {
     return (size_t)k.NS * mega::SLOT_BYTES + 2 * (size_t)k.KVK * 128 * 4 +
-           ((size_t)k.NB * H + k.NB * megab::MAXROWS + k.NB * 128 + mega::NCONS_WARPS * 32 + mega::NCONS_WARPS * k.NB + k.NB +
-            2 * mega::NCONS_WARPS * k.NB + 3 * k.NB + 8) * 4 +
+           (std::max<size_t>((size_t)3 * k.NB * H / 2, megab::ATT_SCRATCH) + k.NB * megab::MAXROWS + k.NB * 128 + mega::NCONS_WARPS * 32 + mega::NCONS_WARPS * k.NB + k.NB +
+            2 * 16 * k.NB + 3 * k.NB + 8) * 4 + (size_t)2 * mega::NCONS_WARPS * (k.NB / 8) * 32 * 16 +
            mega::MAX_LAYERS * sizeof(DecLayerW) + (2 * mega::NSLOT_MAX + 4) * 8 + 128;
 }
 
@@ -790,6 +871,7 @@ bool decode_batch_supported(const Model& m, int B, int ctx) {
     if (B < 2 || c.head_dim != 128) return false;
     if (c.num_attention_heads != 2 * c.num_key_value_heads) return false;
     if (!(bdims_match<1024, 2048, 3072>(c) || bdims_match<256, 512, 512>(c))) return false;
+    if (!m.d_dec_layers_b) return false;
     if (c.num_hidden_layers > 32) return false;
     const int G = m.ctx->sm_count;
     if ((c.hidden_size + G - 1) / G > megab::MAXROWS) return false;
@@ -804,16 +886,21 @@ bool decode_batch_supported(const Model& m, int B, int ctx) {
 size_t decode_batch_part_floats(const Model& m) {
     const asrb_dims& c = m.d.c;
     const size_t NBm = 16;
-    const size_t words = NBm * ((size_t)m.d.qkv_dim + m.d.q_dim + c.hidden_size + c.intermediate_size) +
-                         NBm * c.num_key_value_heads * megab::MAXSPLIT * 2 * mega::PSTRIDE + 64;
+    const size_t words = NBm * (size_t)m.d.qkv_dim + NBm * c.num_key_value_heads * megab::MAXSPLIT * 2 * mega::PSTRIDE + 64;
     return 2 * words + 64;
+}
+// bytes of the self-validating exchange words: 2 sets x layers x 16 sequences x (x after o_proj, x after down_proj, attention
+// output, activations)
+size_t decode_batch_sx_bytes(const Model& m) {
+    const asrb_dims& c = m.d.c;
+    return (size_t)2 * c.num_hidden_layers * 16 * ((size_t)2 * c.hidden_size + m.d.q_dim + c.intermediate_size) * 4;
 }
 
 void launch_decode_step_batch(const Model& m, const DecodeBufs& b, int B, float* kcache, float* vcache,
                               size_t cache_layer_stride, size_t cache_seq_stride, int max_ctx, int ctx_now, const MegaBufs& mb,
                               cudaStream_t st, int64_t* launches) {
     ASRB_REQUIRE(decode_batch_supported(m, B, ctx_now), ASRB_ERR_STATE, "batched fused decode step not supported for this model/batch/context");
-    ASRB_REQUIRE(m.d_dec_layers && mb.bar && mb.part, ASRB_ERR_STATE, "fused decode step buffers missing");
+    ASRB_REQUIRE(m.d_dec_layers_b && m.lm_head_b && mb.bar && mb.part && mb.sx, ASRB_ERR_STATE, "fused decode step buffers missing");
     const asrb_dims& c = m.d.c;
     const int G = m.ctx->sm_count;
     for (int b0 = 0; b0 < B; b0 += 16) {             // passes of up to 16 sequences (weights are streamed once per pass)
@@ -823,13 +910,13 @@ void launch_decode_step_batch(const Model& m, const DecodeBufs& b, int B, float*
         const void* fn = nullptr;
         if (bdims_match<1024, 2048, 3072>(c))
             fn = k.NB == 8 ? (const void*)megab::decode_batch_kernel<1024, 2048, 3072, 8, 3, 64>
-                           : (const void*)megab::decode_batch_kernel<1024, 2048, 3072, 16, 3, 32>;
+                           : (const void*)megab::decode_batch_kernel<1024, 2048, 3072, 16, 2, 32>;
         else
             fn = k.NB == 8 ? (const void*)megab::decode_batch_kernel<256, 512, 512, 8, 3, 64>
-                           : (const void*)megab::decode_batch_kernel<256, 512, 512, 16, 3, 32>;
+                           : (const void*)megab::decode_batch_kernel<256, 512, 512, 16, 2, 32>;
         ASRB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         megab::Params p{};
-        p.layers = m.d_dec_layers; p.lm_head = m.lm_head; p.embed = m.embed; p.final_norm = m.final_norm_sw;
+        p.layers = m.d_dec_layers_b; p.lm_head = m.lm_head_b; p.embed = m.embed; p.final_norm = m.final_norm;
         p.rope_cos = m.rope_cos; p.rope_sin = m.rope_sin; p.eps = (float)c.rms_norm_eps;
         p.L = c.num_hidden_layers; p.H = c.hidden_size; p.QD = m.d.q_dim; p.KVD = m.d.kv_dim; p.I = c.intermediate_size;
         p.V = c.vocab_size; p.nkv = c.num_key_value_heads; p.nb = nb;
@@ -842,10 +929,14 @@ void launch_decode_step_batch(const Model& m, const DecodeBufs& b, int B, float*
         p.bar = mb.bar;
         uint2* w = reinterpret_cast<uint2*>(mb.part);            // 16-byte aligned sub-buffers (even word counts)
         p.qkv_ll = w; w += (size_t)16 * m.d.qkv_dim;
-        p.attn_ll = w; w += (size_t)16 * m.d.q_dim;
-        p.x_ll = w; w += (size_t)16 * c.hidden_size;
-        p.act_ll = w; w += (size_t)16 * c.intermediate_size;
         p.part_ll = w;
+        p.sx = mb.sx;
+        if (mb.sx_nb && *mb.sx_nb != k.NB) {        // region layout depends on NB: re-arm everything when the instantiation changes
+            ASRB_CUDA_CHECK(cudaMemsetAsync(mb.sx, 0xFF, mb.sx_bytes, st));
+            *mb.sx_nb = k.NB;
+        }
+        p.dbg = mb.dbg;
+        g_last_dbg_batch = mb.dbg;
         if (mb.steps_issued && ++*mb.steps_issued >= 0xFFFF00u) {   // tags must stay monotonic: wipe long before the epoch wraps
             ASRB_CUDA_CHECK(cudaMemsetAsync(mb.part, 0, mb.part_bytes, st));
             const unsigned one = 1;

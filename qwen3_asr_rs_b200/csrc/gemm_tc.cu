@@ -18,6 +18,8 @@
 // channels-last layout so that each of the 9 filter taps is a plain (unit-stride) TMA box of a
 // 5-D tensor map; out-of-bounds coordinates (the conv padding) are zero-filled by TMA.
 #include <cuda.h>
+#include <algorithm>
+#include <cstring>
 #include <map>
 #include <tuple>
 #include "internal.h"
@@ -120,7 +122,7 @@ struct ConvGeom { int OH, OW, box_h, tiles_per_chunk, kblk_per_tap, a_box_bytes;
 template <int A_MODE, int EPI_MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               int M, int N, int K, int nplanes, ConvGeom cg, GemmEpi E) {
+               int M, int N, int K, int nplanes, int tiles_m, int tiles_n, int splits, ConvGeom cg, GemmEpi E) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -129,11 +131,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint64_t* acc_empty = acc_full + 2;       // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN;
-    // split-K: gridDim.z CTAs share one output tile, each contracts num_kb k-blocks starting at kb0 and writes its
-    // partial tile to row block blockIdx.z of a [splits][M][N] fp32 workspace (plain epilogue, see launch_gemm_tc)
-    const int num_kb = K / BK / (int)gridDim.z;
-    const int kb0 = (int)blockIdx.z * num_kb;
+    // Persistent CTAs: work item = (m tile, n tile, k split), dealt round-robin (item = blockIdx.x + i * gridDim.x; n
+    // fastest so that concurrently running CTAs share the A tile in L2).  The three roles keep GLOBAL stage / chunk
+    // counters across items, so the TMA producer and the MMA issuer run ahead into the next tile while the epilogue
+    // warps finish the previous one (its final stores overlap the next tile's loads and MMAs through the second TMEM
+    // accumulator); barriers and TMEM are set up once per CTA.
+    // split-K: `splits` items share one output tile, each contracts num_kb k-blocks starting at kb0 and writes its
+    // partial tile to row block z of a [splits][M][N] fp32 workspace (plain epilogue, see launch_gemm_tc)
+    const int num_kb = K / BK / splits;
+    const int n_items = tiles_m * tiles_n * splits;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -151,10 +157,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    // tile coordinates
-    int m0 = blockIdx.y * BM;              // plain
-    int chunk = 0, oh0 = 0;                // conv
-    if (A_MODE == 1) { chunk = blockIdx.y / cg.tiles_per_chunk; oh0 = (blockIdx.y % cg.tiles_per_chunk) * cg.box_h; }
+    // item -> tile coordinates
+    auto item_coords = [&](int item, int& n0, int& m0, int& chunk, int& oh0, int& z) {
+        const int nt = item % tiles_n; int rest = item / tiles_n;
+        const int mt = rest % tiles_m; z = rest / tiles_m;
+        n0 = nt * BN; m0 = mt * BM; chunk = 0; oh0 = 0;
+        if (A_MODE == 1) { chunk = mt / cg.tiles_per_chunk; oh0 = (mt % cg.tiles_per_chunk) * cg.box_h; }
+    };
 
     if (warp == 0 && lane == 0) {
         // ================= TMA producer =================
@@ -162,79 +171,93 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // has OW*box_h (<= 128) rows, the remaining rows of the UMMA tile are never read back.
         const uint32_t a_bytes = (A_MODE == 0) ? (uint32_t)TILE_A_BYTES : (uint32_t)cg.a_box_bytes;
         const uint32_t stage_tx = (uint32_t)nplanes * a_bytes + (uint32_t)TILE_B_BYTES;
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES; const uint32_t par = (kb / STAGES) & 1;
-            mbar_wait(&empty[s], par ^ 1);
-            uint8_t* st = smem + s * STAGE_BYTES;
-            mbar_expect_tx(&full[s], stage_tx);
-            if (A_MODE == 0) {
-                for (int p = 0; p < nplanes; ++p) tma_load_3d(st + p * TILE_A_BYTES, &mapA, (kb0 + kb) * BK, m0, p, &full[s]);
-            } else {
-                const int tap = kb / cg.kblk_per_tap, cb = kb % cg.kblk_per_tap;
-                const int kh = tap / 3, kw = tap % 3;
-                const int ph = (kh == 1) ? 0 : 1, pw = (kw == 1) ? 0 : 1;
-                const int h = oh0 + (kh == 0 ? -1 : 0), w = (kw == 0 ? -1 : 0);
-                for (int p = 0; p < nplanes; ++p)
-                    tma_load_5d(st + p * TILE_A_BYTES, &mapA, cb * BK, w, h, (chunk * 2 + ph) * 2 + pw, p, &full[s]);
+        uint32_t kg = 0;                                   // global k-block counter (ring position)
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int n0, m0, chunk, oh0, z;
+            item_coords(item, n0, m0, chunk, oh0, z);
+            const int kb0 = z * num_kb;
+            for (int kb = 0; kb < num_kb; ++kb, ++kg) {
+                const int s = kg % STAGES; const uint32_t par = (kg / STAGES) & 1;
+                mbar_wait(&empty[s], par ^ 1);
+                uint8_t* st = smem + s * STAGE_BYTES;
+                mbar_expect_tx(&full[s], stage_tx);
+                if (A_MODE == 0) {
+                    for (int p = 0; p < nplanes; ++p) tma_load_3d(st + p * TILE_A_BYTES, &mapA, (kb0 + kb) * BK, m0, p, &full[s]);
+                } else {
+                    const int tap = kb / cg.kblk_per_tap, cb = kb % cg.kblk_per_tap;
+                    const int kh = tap / 3, kw = tap % 3;
+                    const int ph = (kh == 1) ? 0 : 1, pw = (kw == 1) ? 0 : 1;
+                    const int h = oh0 + (kh == 0 ? -1 : 0), w = (kw == 0 ? -1 : 0);
+                    for (int p = 0; p < nplanes; ++p)
+                        tma_load_5d(st + p * TILE_A_BYTES, &mapA, cb * BK, w, h, (chunk * 2 + ph) * 2 + pw, p, &full[s]);
+                }
+                tma_load_2d(st + 3 * TILE_A_BYTES, &mapB, (kb0 + kb) * BK, n0, &full[s]);
             }
-            tma_load_2d(st + 3 * TILE_A_BYTES, &mapB, (kb0 + kb) * BK, n0, &full[s]);
         }
     } else if (warp == 1 && lane == 0) {
         // ================= MMA issuer =================
         const uint32_t idesc = make_idesc();
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES; const uint32_t par = (kb / STAGES) & 1;
-            const int c = kb / CH, cb = c & 1;                          // chunk index / accumulator buffer
-            const bool chunk_first = (kb % CH) == 0;
-            if (chunk_first) { mbar_wait(&acc_empty[cb], ((c >> 1) & 1) ^ 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-            mbar_wait(&full[s], par);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-            const uint64_t bdesc = make_smem_desc(sa + 3 * TILE_A_BYTES);
-            const uint32_t tacc = tmem_base + (uint32_t)(cb * BN);
-            for (int p = 0; p < nplanes; ++p) {
-                const uint64_t adesc = make_smem_desc(sa + p * TILE_A_BYTES);
+        uint32_t kg = 0, cgl = 0;                          // global k-block / chunk counters
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int kb = 0; kb < num_kb; ++kb, ++kg) {
+                const int s = kg % STAGES; const uint32_t par = (kg / STAGES) & 1;
+                const int cb = cgl & 1;                                     // accumulator buffer of the current chunk
+                const bool chunk_first = (kb % CH) == 0;
+                if (chunk_first) { mbar_wait(&acc_empty[cb], ((cgl >> 1) & 1) ^ 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+                mbar_wait(&full[s], par);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t bdesc = make_smem_desc(sa + 3 * TILE_A_BYTES);
+                const uint32_t tacc = tmem_base + (uint32_t)(cb * BN);
+                for (int p = 0; p < nplanes; ++p) {
+                    const uint64_t adesc = make_smem_desc(sa + p * TILE_A_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)     // +32 B per K=16 step inside the 128 B swizzle atom
-                    umma(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, !(chunk_first && p == 0 && k == 0));
+                    for (int k = 0; k < BK / 16; ++k)     // +32 B per K=16 step inside the 128 B swizzle atom
+                        umma(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, !(chunk_first && p == 0 && k == 0));
+                }
+                umma_commit(&empty[s]);                   // slot reusable once these MMAs retire
+                if ((kb % CH) == CH - 1 || kb == num_kb - 1) { umma_commit(&acc_full[cb]); ++cgl; }
             }
-            umma_commit(&empty[s]);                   // slot reusable once these MMAs retire
-            if ((kb % CH) == CH - 1 || kb == num_kb - 1) umma_commit(&acc_full[cb]);
         }
     } else if (warp >= 2) {
         // ================= epilogue =================
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
         const int r = quad * 32 + lane;               // row inside the tile
-        float accum[BN];
-#pragma unroll
-        for (int j = 0; j < BN; ++j) accum[j] = 0.f;
         const int num_chunks = (num_kb + CH - 1) / CH;
-        for (int c = 0; c < num_chunks; ++c) {
-            const int cb = c & 1;
-            mbar_wait(&acc_full[cb], (c >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t cgl = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int n0, m0, chunk, oh0, z;
+            item_coords(item, n0, m0, chunk, oh0, z);
+            float accum[BN];
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * BN + c0), v);
+            for (int j = 0; j < BN; ++j) accum[j] = 0.f;
+            for (int c = 0; c < num_chunks; ++c, ++cgl) {
+                const int cb = cgl & 1;
+                mbar_wait(&acc_full[cb], (cgl >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 32; ++j) accum[c0 + j] += __uint_as_float(v[j]);
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * BN + c0), v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) accum[c0 + j] += __uint_as_float(v[j]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[cb])) : "memory");
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[cb])) : "memory");
-        }
-        long long m = -1;
-        if (A_MODE == 0) { if (m0 + r < M) m = m0 + r + (long long)blockIdx.z * M; }
-        else {
-            const int oh = oh0 + r / cg.OW, ow = r % cg.OW;
-            if (r < cg.box_h * cg.OW && oh < cg.OH) m = ((long long)chunk * cg.OH + oh) * cg.OW + ow;
-        }
-        if (m >= 0) {
+            long long m = -1;
+            if (A_MODE == 0) { if (m0 + r < M) m = m0 + r + (long long)z * M; }
+            else {
+                const int oh = oh0 + r / cg.OW, ow = r % cg.OW;
+                if (r < cg.box_h * cg.OW && oh < cg.OH) m = ((long long)chunk * cg.OH + oh) * cg.OW + ow;
+            }
+            if (m >= 0) {
 #pragma unroll
-            for (int j = 0; j < BN; j += 8) {
-                const int n = n0 + j;
-                if (n < N) epi_store8<EPI_MODE>(E, N, (int)m, n, &accum[j]);
+                for (int j = 0; j < BN; j += 8) {
+                    const int n = n0 + j;
+                    if (n < N) epi_store8<EPI_MODE>(E, N, (int)m, n, &accum[j]);
+                }
             }
         }
     }
@@ -288,6 +311,32 @@ static CUtensorMap make_map(const void* base, int rank, const cuuint64_t* dims, 
     return m;
 }
 
+// Tensor maps depend only on (base, shape, strides, box): encode once per distinct operand instead of on every launch
+// (a clip issues ~400 GEMMs over a few dozen distinct operands).  Thread-local: sessions on different host threads.
+struct MapKey {
+    const void* base; int rank; cuuint64_t d[5]; cuuint64_t s[4]; cuuint32_t b[5];
+    bool operator<(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) < 0; }
+};
+static const CUtensorMap& cached_map(const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    static thread_local std::map<MapKey, CUtensorMap> cache;
+    MapKey k;
+    memset(&k, 0, sizeof(k));
+    k.base = base; k.rank = rank;
+    for (int i = 0; i < rank; ++i) { k.d[i] = dims[i]; k.b[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) k.s[i] = strides_bytes[i];
+    auto it = cache.find(k);
+    if (it == cache.end()) {
+        if (cache.size() > 4096) cache.clear();
+        it = cache.emplace(k, make_map(base, rank, dims, strides_bytes, box)).first;
+    }
+    return it->second;
+}
+
+static int sm_count() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
 static size_t smem_bytes() { return (size_t)STAGES * STAGE_BYTES + 1024 + 256; }   // stages + alignment slack + barriers
 
 }  // namespace tc
@@ -301,7 +350,7 @@ bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& E, cuda
     cuuint64_t bd[2] = {(cuuint64_t)A.K, (cuuint64_t)N};
     cuuint64_t bs[1] = {(cuuint64_t)A.K * 2};
     cuuint32_t bb[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
-    CUtensorMap mapB = make_map(W, 2, bd, bs, bb);
+    const CUtensorMap mapB = cached_map(W, 2, bd, bs, bb);
     ConvGeom cg{};
     const size_t smem = smem_bytes();
     if (N % 8 != 0) return false;
@@ -310,13 +359,14 @@ bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& E, cuda
         cuuint64_t ad[3] = {(cuuint64_t)A.K, (cuuint64_t)A.M, (cuuint64_t)3};
         cuuint64_t as[2] = {(cuuint64_t)A.lda * 2, (cuuint64_t)A.plane_stride * 2};
         cuuint32_t ab[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1};
-        CUtensorMap mapA = make_map(A.a, 3, ad, as, ab);
-        dim3 grid((N + BN - 1) / BN, (A.M + BM - 1) / BM);
+        const CUtensorMap mapA = cached_map(A.a, 3, ad, as, ab);
+        const int tiles_n = (N + BN - 1) / BN, tiles_m = (A.M + BM - 1) / BM;
+        const int sms = sm_count();
         // Split-K for plain GEMMs that cannot fill the GPU (e.g. prefill o_proj / down_proj: 32 tiles, K = 2048 / 3072;
         // encoder fc2: 28 tiles, K = 3584): such a CTA is bound by its own TMA load rate (64 KB of operands per k-block),
         // so 2-4 CTAs per tile finish 2-4x sooner; a second pass sums the partial tiles (fixed order) and applies the
         // epilogue.  Deterministic; costs one extra fp32 round trip of the tile through L2.
-        const int tiles = (int)(grid.x * grid.y), kblocks = A.K / BK;
+        const int tiles = tiles_n * tiles_m, kblocks = A.K / BK;
         int splits = 1;
         if (E.mode == EPI_PLAIN && E.splitk_ws && tiles <= 64 && N % 8 == 0 && (size_t)4 * A.M * N <= SPLITK_WS_FLOATS) {
             for (int sp = 4; sp >= 2; --sp)
@@ -325,10 +375,9 @@ bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& E, cuda
         if (splits > 1) {
             GemmEpi P;                               // partial tiles: plain fp32 rows [split][M][N]
             P.out_f32 = E.splitk_ws; P.ldo = N;
-            grid.z = splits;
-            static bool attr_s = false;
-            if (!attr_s) { ASRB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<0, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_s = true; }
-            gemm_tc_kernel<0, EPI_PLAIN><<<grid, NTHREADS, smem, st>>>(mapA, mapB, A.M, N, A.K, A.nplanes, cg, P);
+            // (the attribute is per device: set on every launch, a process may hold contexts on several GPUs)
+            ASRB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<0, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gemm_tc_kernel<0, EPI_PLAIN><<<std::min(tiles * splits, sms), NTHREADS, smem, st>>>(mapA, mapB, A.M, N, A.K, A.nplanes, tiles_m, tiles_n, splits, cg, P);
             const int work = A.M * (N / 8);
             splitk_reduce_kernel<<<(work + 255) / 256, 256, 0, st>>>(E.splitk_ws, splits, A.M, N, E);
             ASRB_CUDA_CHECK(cudaGetLastError());
@@ -337,9 +386,8 @@ bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& E, cuda
         }
 #define ASRB_TC_LAUNCH(AM, EM)                                                                                         \
     {                                                                                                                  \
-        static bool attr = false;                                                                                      \
-        if (!attr) { ASRB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<AM, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
-        gemm_tc_kernel<AM, EM><<<grid, NTHREADS, smem, st>>>(mapA, mapB, A.M, N, A.K, A.nplanes, cg, E);                \
+        ASRB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<AM, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        gemm_tc_kernel<AM, EM><<<std::min(tiles_m * tiles_n, sms), NTHREADS, smem, st>>>(mapA, mapB, A.M, N, A.K, A.nplanes, tiles_m, tiles_n, 1, cg, E); \
     }
         if (E.mode == EPI_PLAIN) ASRB_TC_LAUNCH(0, EPI_PLAIN)
         else if (E.mode == EPI_SWIGLU) ASRB_TC_LAUNCH(0, EPI_SWIGLU)
@@ -357,8 +405,9 @@ bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& E, cuda
         cuuint64_t as[4] = {(cuuint64_t)A.cpad * 2, (cuuint64_t)A.Wh * A.cpad * 2, (cuuint64_t)A.Hh * A.Wh * A.cpad * 2,
                             (cuuint64_t)A.plane_stride * 2};
         cuuint32_t ab[5] = {(cuuint32_t)BK, (cuuint32_t)A.OW, (cuuint32_t)cg.box_h, 1, 1};
-        CUtensorMap mapA = make_map(A.a, 5, ad, as, ab);
-        dim3 grid((N + BN - 1) / BN, chunks * cg.tiles_per_chunk);
+        const CUtensorMap mapA = cached_map(A.a, 5, ad, as, ab);
+        const int tiles_n = (N + BN - 1) / BN, tiles_m = chunks * cg.tiles_per_chunk;
+        const int sms = sm_count();
         if (E.mode == EPI_CONV_PARITY) ASRB_TC_LAUNCH(1, EPI_CONV_PARITY)
         else if (E.mode == EPI_CONV_FEAT) ASRB_TC_LAUNCH(1, EPI_CONV_FEAT)
         else return false;

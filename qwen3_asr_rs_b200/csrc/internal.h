@@ -25,6 +25,7 @@ struct Dims {
     int q_dim, kv_dim, qkv_dim;
     void derive();
 };
+void validate_dims(const asrb_dims& d);   // c_api.cu: throws ASRB_ERR_INVALID
 inline int conv_out_len(int l) { return (l - 1) / 2 + 1; }   // audio_encoder.rs:263-266
 
 struct Ctx {
@@ -54,7 +55,8 @@ struct Model {
     Ctx* ctx = nullptr;
     Dims d;
     bool finalized = false;
-    bool lossy_weights = false;          // an F32/F16 matrix was not bf16-representable
+    bool lossy_weights = false;          // an F32/F16 matrix was not bf16-representable (only with ASRB_ALLOW_LOSSY_WEIGHTS=1)
+    int lossy_count = 0;
     std::map<std::string, RawTensor> raw;
     std::vector<void*> owned;            // packed buffers created at finalize
 
@@ -75,6 +77,10 @@ struct Model {
     DecLayerW* d_dec_layers = nullptr;   // device copy of `dec` for the fused decode step; its ln_in / ln_post point at
                                          // copies stored in the step's bank-conflict-free activation layout (decode_mega.cu)
     float* final_norm_sw = nullptr;      // final norm weight in the same layout
+    // batch-aware fused step (decode_batch.cu): weight matrices with the 16-byte chunks of every row XOR-swizzled by
+    // (row & 7) -- bank-conflict-free ldmatrix on bulk-copied rows -- and plain norm vectors; null for unsupported dims
+    DecLayerW* d_dec_layers_b = nullptr;
+    bf16* lm_head_b = nullptr;
     float *rope_cos = nullptr, *rope_sin = nullptr;   // [rope_max_pos][head_dim/2]
     int rope_max_pos = 0;
 
@@ -181,9 +187,11 @@ void launch_decode_step_phases(const Model& m, const DecodeBufs& b, int B, float
                                bool write_logits, cudaStream_t st, int64_t* launches);
 // final-norm + lm_head + argmax on arbitrary rows of a residual stream (prefill last rows);
 // also performs the greedy bookkeeping of src/inference.rs:161-170 (EOS check, append, embed)
-struct MegaBufs { unsigned* bar = nullptr; float* part = nullptr; long long* dbg = nullptr; size_t part_bytes = 0; unsigned* steps_issued = nullptr; };   // per-session state of the fused step
+struct MegaBufs { unsigned* bar = nullptr; float* part = nullptr; long long* dbg = nullptr; size_t part_bytes = 0; unsigned* steps_issued = nullptr;
+                  uint32_t* sx = nullptr; size_t sx_bytes = 0; int* sx_nb = nullptr; };   // sx: decode_batch.cu's self-validating words   // per-session state of the fused step
 size_t decode_mega_part_floats(const Model& m);
-size_t decode_batch_part_floats(const Model& m);   // decode_batch.cu: NB sequences per fused launch
+size_t decode_batch_part_floats(const Model& m);
+size_t decode_batch_sx_bytes(const Model& m);   // decode_batch.cu: NB sequences per fused launch
 bool decode_batch_supported(const Model& m, int B, int ctx);
 int decode_mega_dbg_slots();
 void launch_greedy(const Model& m, const DecodeBufs& b, int B, cudaStream_t st, int64_t* launches);

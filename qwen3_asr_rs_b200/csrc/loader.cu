@@ -185,6 +185,7 @@ void model_load_dir(Ctx* ctx, const char* dir_c, Model** out) {
     geti(t, "num_key_value_heads", d.num_key_value_heads); geti(t, "head_dim", d.head_dim);
     getd(t, "rms_norm_eps", d.rms_norm_eps); getd(t, "rope_theta", d.rope_theta);
     if (t) if (const JVal* tw = t->get("tie_word_embeddings")) if (tw->kind == JVal::Bool) d.tie_word_embeddings = tw->b ? 1 : 0;
+    validate_dims(d);                      // a config.json with n_window = 0 etc. must be a status code, not a SIGFPE
     m->ctx = ctx; m->d.c = d; m->d.derive();
     // ---- weights (weights.rs:10-58) ----
     const std::string single = dir + "/model.safetensors", index = dir + "/model.safetensors.index.json";

@@ -56,6 +56,17 @@ static bool is_matrix_name(const std::string& name, int ndim) {
     return true;
 }
 
+// Matrices are stored as bf16 (exact for the released bf16 checkpoints, which the reference widens to f32,
+// weights.rs:74-89).  An F32 / F16 matrix that is NOT bf16-representable would silently change logits and ids, so it is
+// an error unless ASRB_ALLOW_LOSSY_WEIGHTS=1, in which case it is rounded (RNE) and counted (asrb_model_lossy_tensors).
+static void note_lossy(Model* m, const std::string& name) {
+    const char* e = getenv("ASRB_ALLOW_LOSSY_WEIGHTS");
+    if (!(e && e[0] == '1'))
+        throw Error(ASRB_ERR_INVALID, "tensor " + name + " is not bf16-representable: this library keeps matrices in bf16 (exact for bf16 "
+                                      "checkpoints); set ASRB_ALLOW_LOSSY_WEIGHTS=1 to round it (results then differ from the f32 reference)");
+    m->lossy_weights = true; m->lossy_count += 1;
+}
+
 void model_set_tensor(Model* m, const char* name_c, int dtype, const int64_t* shape, int ndim, const void* host) {
     ASRB_REQUIRE(!m->finalized, ASRB_ERR_STATE, "model already finalized");
     ASRB_REQUIRE(name_c && host && ndim >= 1 && ndim <= 4, ASRB_ERR_INVALID, "set_tensor: bad arguments");
@@ -74,12 +85,12 @@ void model_set_tensor(Model* m, const char* name_c, int dtype, const int64_t* sh
         if (dtype == ASRB_DT_F32) {
             tmp.resize(numel); bool inexact = false; const float* f = (const float*)host;
             for (size_t i = 0; i < numel; ++i) tmp[i] = f32_to_bf16_rne(f[i], &inexact);
-            if (inexact) m->lossy_weights = true;
+            if (inexact) note_lossy(m, name);
             src = tmp.data();
         } else if (dtype == ASRB_DT_F16) {
             tmp.resize(numel); bool inexact = false; const uint16_t* h = (const uint16_t*)host;
             for (size_t i = 0; i < numel; ++i) tmp[i] = f32_to_bf16_rne(f16_to_f32(h[i]), &inexact);
-            if (inexact) m->lossy_weights = true;
+            if (inexact) note_lossy(m, name);
             src = tmp.data();
         } else ASRB_REQUIRE(dtype == ASRB_DT_BF16, ASRB_ERR_INVALID, "set_tensor: unsupported dtype");
         ASRB_CUDA_CHECK(cudaMalloc(&t.dev, numel * 2));
@@ -130,6 +141,25 @@ template <typename T> static T* dev_alloc(Model* m, size_t n) {
     ASRB_CUDA_CHECK(cudaMalloc(&p, n * sizeof(T)));
     m->owned.push_back(p);
     return p;
+}
+
+// Copy of a bf16 [N][K] matrix with the 16-byte chunks of row r stored at chunk index (c & ~7) | ((c ^ r) & 7): rows that
+// are bulk-copied into shared memory at a 2 KB pitch then feed ldmatrix without bank conflicts (decode_batch.cu)
+__global__ void swizzle_rows_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n_rows, int chunks) {
+    const size_t total = n_rows * (size_t)chunks;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / chunks; const int cc = (int)(i - r * chunks);
+        out[r * chunks + ((cc & ~7) | ((cc ^ (int)(r & 7)) & 7))] = in[i];
+    }
+}
+static bf16* swizzled_rows_copy(Model* m, const bf16* src, size_t n_rows, int K) {
+    ASRB_REQUIRE(K % 64 == 0, ASRB_ERR_INVALID, "swizzled copy needs K % 64 == 0");
+    bf16* dst = nullptr;
+    ASRB_CUDA_CHECK(cudaMalloc(&dst, n_rows * (size_t)K * 2));
+    m->owned.push_back(dst);
+    swizzle_rows_kernel<<<1184, 256>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), n_rows, K / 8);
+    ASRB_CUDA_CHECK(cudaGetLastError());
+    return dst;
 }
 
 // Copy of an fp32 vector in the activation layout of the fused decode step (decode_mega.cu, xs_swz): 16-byte group k
@@ -333,6 +363,20 @@ void model_finalize(Model* m) {
         m->final_norm_sw = swizzled_copy(m, m->final_norm, (int)H);
         m->d_dec_layers = dev_alloc<DecLayerW>(m, tab.size());
         ASRB_CUDA_CHECK(cudaMemcpy(m->d_dec_layers, tab.data(), tab.size() * sizeof(DecLayerW), cudaMemcpyHostToDevice));
+    }
+    // chunk-swizzled weight copies for the batch-aware fused step (dims it is instantiated for: 0.6B and the test config)
+    if (c.head_dim == 128 && c.num_attention_heads == 2 * c.num_key_value_heads &&
+        ((H == 1024 && qd == 2048 && I == 3072) || (H == 256 && qd == 512 && I == 512))) {
+        std::vector<DecLayerW> tab = m->dec;
+        for (DecLayerW& w : tab) {
+            w.wqkv = swizzled_rows_copy(m, w.wqkv, (size_t)d.qkv_dim, (int)H);
+            w.wo = swizzled_rows_copy(m, w.wo, (size_t)H, (int)qd);
+            w.wgu = swizzled_rows_copy(m, w.wgu, (size_t)2 * I, (int)H);
+            w.wdown = swizzled_rows_copy(m, w.wdown, (size_t)H, (int)I);
+        }
+        m->lm_head_b = swizzled_rows_copy(m, m->lm_head, (size_t)V, (int)H);
+        m->d_dec_layers_b = dev_alloc<DecLayerW>(m, tab.size());
+        ASRB_CUDA_CHECK(cudaMemcpy(m->d_dec_layers_b, tab.data(), tab.size() * sizeof(DecLayerW), cudaMemcpyHostToDevice));
     }
     build_mel_tables(m);
     build_pos_tables(m);

@@ -50,6 +50,7 @@ struct Session {
     DecodeBufs db{};
     float* splitk_ws = nullptr;   // fp32 partial tiles of split-K GEMMs (gemm_tc.cu)
     MegaBufs mega{};
+    int sx_nb = 0;             // NB instantiation the exchange words were last armed for (decode_batch.cu)
     unsigned mega_steps = 1;   // host mirror of the device epoch (upper bound): see launch_decode_step_mega
     int* d_lastrow = nullptr;
     int *h_done = nullptr, *h_ids = nullptr, *h_nout = nullptr, *h_next = nullptr;
@@ -168,6 +169,27 @@ Session* session_create(Model* m, int max_batch, int64_t max_samples, int max_la
         s->mega.part = salloc<float>(s, part_floats, true);   // zero = tag 0 = never written
         s->mega.part_bytes = part_floats * sizeof(float);
         s->mega.steps_issued = &s->mega_steps;
+        if (max_batch >= 2) {   // batch-aware fused step: self-validating exchange words, all "not written yet" (0xFFFFFFFF)
+            s->mega.sx_bytes = decode_batch_sx_bytes(*m);
+            s->mega.sx = (uint32_t*)salloc<uint8_t>(s, s->mega.sx_bytes);
+            ASRB_CUDA_CHECK(cudaMemset(s->mega.sx, 0xFF, s->mega.sx_bytes));
+            s->mega.sx_nb = &s->sx_nb;
+            // keep them L2-resident between steps (2-3 GB of weights and KV stream through L2 every step): persisting
+            // access window on the session stream; best effort (ignored if the device refuses the set-aside)
+            int maxwin = 0, maxpersist = 0;
+            cudaDeviceGetAttribute(&maxwin, cudaDevAttrMaxAccessPolicyWindowSize, m->ctx->device);
+            cudaDeviceGetAttribute(&maxpersist, cudaDevAttrMaxPersistingL2CacheSize, m->ctx->device);
+            if (maxwin > 0 && maxpersist > 0) {
+                const size_t want = std::min<size_t>({s->mega.sx_bytes, (size_t)maxwin, (size_t)maxpersist});
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                    cudaStreamAttrValue av{};
+                    av.accessPolicyWindow.base_ptr = s->mega.sx; av.accessPolicyWindow.num_bytes = want;
+                    av.accessPolicyWindow.hitRatio = 1.0f; av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    if (cudaStreamSetAttribute(s->st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+                } else cudaGetLastError();
+            }
+        }
         if (getenv("ASRB_MEGA_DEBUG")) s->mega.dbg = salloc<long long>(s, decode_mega_dbg_slots(), true);
         ASRB_CUDA_CHECK(cudaMallocHost(&s->h_done, Bm * sizeof(int)));
         ASRB_CUDA_CHECK(cudaMallocHost(&s->h_nout, Bm * sizeof(int)));
@@ -496,7 +518,7 @@ void session_generate(Session* s, int max_new_tokens, int32_t* ids_out, int32_t*
     // (inference.rs:160-200); that wasted forward is not issued here.
     const int steps = std::max(0, max_new_tokens - s->greedy_done);
     auto ensure_graph = [&]() {   // per-phase path: ~142 launches per step -> replay them as one CUDA graph
-        const int mode_key = s->decode_mode * 16 + B;
+        const int mode_key = s->decode_mode * (s->max_batch + 1) + B;     // unique per (mode, batch)
         if (s->step_graph == nullptr || s->graph_mode != mode_key) {
             if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = nullptr; }
             cudaGraph_t g = nullptr;
@@ -564,6 +586,11 @@ void session_last_timings(Session* s, float* ms6, int64_t* kernels, int64_t* ste
     if (steps) *steps = s->decode_steps;
 }
 
+void session_device_ids(Session* s, const int32_t** ids, const int32_t** lens, int* stride, int* batch) {
+    ASRB_REQUIRE(s->stage >= 3, ASRB_ERR_STATE, "device_ids: nothing generated yet");
+    *ids = s->db.ids_out; *lens = s->db.n_out; *stride = s->max_new; *batch = s->B;
+}
+
 void session_stats(Session* s, int64_t* out, int n) {
     const int64_t v[5] = {s->n_batch_steps, s->n_mega_steps, s->n_phase_steps, g_gemm_simt_fallbacks.load(), g_gemm_tc_launches.load()};
     for (int i = 0; i < n && i < 5; ++i) out[i] = v[i];
@@ -571,6 +598,7 @@ void session_stats(Session* s, int64_t* out, int n) {
 
 void session_set_option(Session* s, const char* key, const char* value) {
     std::string k(key ? key : ""), v(value ? value : "");
+    if (s->step_graph) { cudaGraphExecDestroy(s->step_graph); s->step_graph = nullptr; s->graph_mode = -1; }   // captured with the old options
     if (k == "gemm") {
         if (v == "tc") s->gemm_impl = GEMM_TC; else if (v == "simt") s->gemm_impl = GEMM_SIMT;
         else throw Error(ASRB_ERR_INVALID, "gemm must be tc|simt");

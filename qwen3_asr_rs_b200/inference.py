@@ -144,6 +144,13 @@ class AsrInference:
         if self._session is not None:
             _lib.check(self._lib.asrb_session_set_option(self._session, key.encode(), value.encode()))
 
+    def device_ids(self):
+        """(ids_ptr, lens_ptr, row_stride, batch): device addresses of the last generated ids (asrb_session_device_ids)."""
+        ids, lens = C.c_void_p(), C.c_void_p()
+        stride, batch = C.c_int(), C.c_int()
+        _lib.check(self._lib.asrb_session_device_ids(self._session, C.byref(ids), C.byref(lens), C.byref(stride), C.byref(batch)))
+        return ids.value, lens.value, stride.value, batch.value
+
     def stats(self) -> Dict[str, int]:
         """Decoder-forward / GEMM path counters (asrb_session_stats): fallbacks are visible, never silent."""
         out = (C.c_int64 * 5)()

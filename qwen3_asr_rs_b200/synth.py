@@ -20,9 +20,18 @@ def _bf16(t: torch.Tensor) -> torch.Tensor:
     return t.to(torch.bfloat16)
 
 
-def make_weights(cfg, seed: int = 0) -> Dict[str, torch.Tensor]:
+def make_weights(cfg, seed: int = 0, peaked_head: bool = False) -> Dict[str, torch.Tensor]:
     """Returns name -> bf16 tensor.  ``cfg`` is any object with .audio / .text dims
-    (oracle.AsrCfg or qwen3_asr_rs_b200.config.AsrConfig)."""
+    (oracle.AsrCfg or qwen3_asr_rs_b200.config.AsrConfig).
+
+    Random weights give near-flat logits: the top-1/top-2 gap of a tied random head is a few 1e-5 of max|logit| at
+    its worst step, the same size as fp32 summation-order noise, so exact-id parity becomes a coin toss for reasons
+    unrelated to kernel correctness.  ``peaked_head=True`` (needs
+    ``cfg.text.tie_word_embeddings == False``, the untied key of src/text_decoder.rs:75-79) draws the lm_head rows
+    with log-normal norms (sigma 0.5): logits are dominated by a few hundred large-norm rows, the winner still depends
+    on the hidden state's direction (dozens of distinct ids per 128 tokens), and the measured worst gap is >= 2e-4 of
+    max|logit| -- an order of magnitude above the noise.  The embedding stays plain, so there is no self-token
+    fixed point (a tied peaked head repeats one id forever)."""
     g = torch.Generator().manual_seed(seed)
     a, t = cfg.audio, cfg.text
     w: Dict[str, torch.Tensor] = {}
@@ -83,7 +92,14 @@ def make_weights(cfg, seed: int = 0) -> Dict[str, torch.Tensor]:
         w[f"{q}.mlp.down_proj.weight"] = rn(H, I, std=2.0 / I ** 0.5)
     w[f"{p}.norm.weight"] = norm_w(H)
     if not t.tie_word_embeddings:
-        w["thinker.lm_head.weight"] = rn(t.vocab_size, H, std=0.1)
+        if peaked_head:
+            g2 = torch.Generator().manual_seed(4242 + seed)
+            e = torch.randn(t.vocab_size, H, generator=g2, dtype=torch.float32) * 0.1
+            w["thinker.lm_head.weight"] = _bf16(e * torch.exp(0.5 * torch.randn(t.vocab_size, 1, generator=g2, dtype=torch.float32)))
+        else:
+            w["thinker.lm_head.weight"] = rn(t.vocab_size, H, std=0.1)
+    else:
+        assert not peaked_head, "peaked_head needs an untied lm_head (cfg.text.tie_word_embeddings = False)"
     return w
 
 

@@ -42,6 +42,7 @@ extern "C" {
     pub fn asrb_model_set_tensor(m: *mut asrb_model, name: *const c_char, dtype: c_int, shape: *const i64, ndim: c_int, host_data: *const c_void) -> c_int;
     pub fn asrb_model_finalize(m: *mut asrb_model) -> c_int;
     pub fn asrb_model_dims(m: *const asrb_model, out: *mut AsrbDims) -> c_int;
+    pub fn asrb_model_lossy_tensors(m: *const asrb_model, count: *mut c_int) -> c_int;
     pub fn asrb_model_free(m: *mut asrb_model) -> c_int;
 
     pub fn asrb_session_create(m: *mut asrb_model, max_batch: c_int, max_samples: i64, max_lang_ids: c_int, max_new_tokens: c_int, out: *mut *mut asrb_session) -> c_int;
@@ -58,6 +59,7 @@ extern "C" {
     pub fn asrb_generate(s: *mut asrb_session, max_new_tokens: c_int, ids_out: *mut i32, lens_out: *mut i32) -> c_int;
 
     pub fn asrb_last_timings(s: *mut asrb_session, ms_out6: *mut f32, kernels_launched: *mut i64, decode_steps: *mut i64) -> c_int;
+    pub fn asrb_session_device_ids(s: *mut asrb_session, ids_dev: *mut *const i32, lens_dev: *mut *const i32, row_stride: *mut c_int, batch: *mut c_int) -> c_int;
     pub fn asrb_session_stats(s: *mut asrb_session, out: *mut i64, n: c_int) -> c_int;
     pub fn asrb_session_set_option(s: *mut asrb_session, key: *const c_char, value: *const c_char) -> c_int;
     pub fn asrb_debug_mega_timeline(out: *mut c_longlong, cap: c_int) -> c_int;

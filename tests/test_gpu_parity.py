@@ -321,3 +321,172 @@ def test_transcribe_file_end_to_end(tiny, tmp_path):
     # "language English" -> two unknown words -> unk id 0 twice
     ref_forced = O.transcribe_ids(model, samples, language_ids=[0, 0], max_new_tokens=8)
     assert forced.language == "forced" and forced.ids == ref_forced.ids
+
+
+# ------------------------------------------------------------------------------------------------------
+# batch-aware fused decode step (decode_batch.cu) and full-size batches
+# ------------------------------------------------------------------------------------------------------
+NOISE_REL = 1.5e-5      # measured logits deviation vs the oracle (summation order), relative to max|logit|
+MARGIN_FLOOR_REL = 4 * NOISE_REL   # an exact-id comparison is only meaningful above this top-1/top-2 gap
+
+
+def _min_rel_margin(ref):
+    ls = [ref.prefill_logits] + ref.step_logits[:-1]
+    gaps = [float(l.topk(2).values[0] - l.topk(2).values[1]) for l in ls]
+    mx = max(float(l.abs().max()) for l in ls)
+    return min(gaps) / mx
+
+
+@pytest.mark.parametrize("secs", [[2.5, 5.0], [2.5, 9.1, 5.0], [1.1, 2.3, 0.7, 4.9, 3.1, 1.9, 2.2, 0.9],
+                                  [1.1, 2.3, 0.7, 4.9, 3.1, 1.9, 2.2, 0.9, 5.3], [12.0] * 16, [30.0, 12.0, 20.0, 3.0, 25.0]])
+def test_batch_step_tiny(tiny, tiny_engine, secs):
+    """decode_batch.cu (weights streamed once for all sequences): ragged batches of 2..16, NB = 8 and 16 instantiations,
+    one and several 64 / 32-key attention splits per sequence -- ids equal the oracle's AND the per-sequence fused step's."""
+    _, _, model = tiny
+    clips = [synth.make_clip(400 + i, s) for i, s in enumerate(secs)]
+    n_new = 14
+    try:
+        tiny_engine.set_option("batch_step", "1")
+        before = tiny_engine.stats().get("decode_batch_steps", 0)
+        got = tiny_engine.transcribe_ids(clips, max_new_tokens=n_new).ids
+        assert tiny_engine.stats()["decode_batch_steps"] == before + n_new - 1      # the batched kernel really ran
+        tiny_engine.set_option("batch_step", "0")
+        per_seq = tiny_engine.transcribe_ids(clips, max_new_tokens=n_new).ids
+    finally:
+        tiny_engine.set_option("batch_step", "1")
+    assert got == per_seq
+    for g, c in zip(got, clips):
+        assert g == O.transcribe_ids(model, c, max_new_tokens=n_new).ids
+
+
+def test_peaked_untied_head_tiny(report):
+    """Untied lm_head (the `thinker.lm_head.weight` key, src/text_decoder.rs:75-79) with peaked logits (synth.make_weights
+    peaked_head): exact ids with a top-1/top-2 gap well above summation-order noise, batch 1 (fused step) and batch 5."""
+    from qwen3_asr_rs_b200 import AsrInference, config_tiny
+    cfg = O.cfg_tiny()
+    cfg.text.tie_word_embeddings = False
+    w = synth.make_weights(cfg, 7, peaked_head=True)
+    model = O.OracleModel(cfg, w)
+    ecfg = config_tiny()
+    ecfg.text.tie_word_embeddings = False
+    eng = AsrInference.from_weights(ecfg, w, device=0)
+    try:
+        clips = [synth.make_clip(500 + i, s) for i, s in enumerate([4.0, 12.3, 0.8, 7.7, 2.2])]
+        refs = [O.transcribe_ids(model, c, max_new_tokens=40, keep_logits=True) for c in clips]
+        report["peaked_tiny_min_rel_margin"] = min(_min_rel_margin(r) for r in refs)
+        assert report["peaked_tiny_min_rel_margin"] >= MARGIN_FLOOR_REL
+        assert eng.transcribe_ids(clips[:1], max_new_tokens=40).ids[0] == refs[0].ids
+        got = eng.transcribe_ids(clips, max_new_tokens=40).ids
+        for g, r in zip(got, refs):
+            assert g == r.ids
+        assert len({i for r in refs for i in r.ids}) > 20          # not a degenerate one-token model
+    finally:
+        eng.close()
+
+
+@pytest.fixture(scope="module")
+def full_peaked():
+    """Qwen3-ASR-0.6B dims, synthetic weights with the peaked untied head: (oracle model, engine)."""
+    from qwen3_asr_rs_b200 import AsrInference, config_0p6b
+    cfg = O.cfg_0p6b()
+    cfg.text.tie_word_embeddings = False
+    w = synth.make_weights(cfg, 1, peaked_head=True)
+    ecfg = config_0p6b()
+    ecfg.text.tie_word_embeddings = False
+    eng = AsrInference.from_weights(ecfg, w, device=0)
+    yield O.OracleModel(cfg, w), eng
+    eng.close()
+
+
+def test_full_size_0p6b_batch8_30s_128_tokens(full_peaked, report):
+    """north_star shape: Qwen3-ASR-0.6B, batch 8 x 30 s, 128 new tokens per clip -- exact ids for every clip through the
+    batch-aware fused decode step (and the batch-8 encoder / prefill GEMMs), logits within tolerance."""
+    model, eng = full_peaked
+    clips = [synth.make_clip(i, 30.0) for i in range(8)]
+    refs = [O.transcribe_ids(model, c, max_new_tokens=128, keep_logits=True, lm_head_all_rows=False) for c in clips]
+    report["full_b8_min_rel_margin"] = min(_min_rel_margin(r) for r in refs)
+    eng.mel(clips)
+    eng.encode()
+    _, logits = eng.prefill()
+    report["full_b8_prefill_logits_rel_err"] = max(_rel(logits[b], refs[b].prefill_logits.numpy()) for b in range(8))
+    before = eng.stats().get("decode_batch_steps", 0)
+    got = eng.transcribe_ids(clips, max_new_tokens=128)
+    st = eng.stats()
+    report["full_b8_stage_ms"] = got.stage_ms
+    assert report["full_b8_min_rel_margin"] >= MARGIN_FLOOR_REL
+    assert report["full_b8_prefill_logits_rel_err"] <= LOGIT_RTOL
+    assert st["decode_batch_steps"] == before + 127 and st["gemm_simt_fallbacks"] == 0
+    for b in range(8):
+        assert got.ids[b] == refs[b].ids, b
+
+
+def test_full_size_0p6b_16_sequences_512_token_kv(full_peaked, report):
+    """BASELINE configs[4] per GPU: 16 sequences decoding around a 512-token KV cache (prompts of 300..405 tokens +
+    128 new tokens cross 512 for the long ones), ragged lengths -- exact ids for every sequence (NB = 16 instantiation,
+    32-key attention splits, up to 17 splits per kv head)."""
+    model, eng = full_peaked
+    secs = [30.0, 22.6, 27.7, 30.0, 24.1, 29.2, 30.0, 21.3, 26.4, 30.0, 28.8, 23.5, 30.0, 25.9, 29.9, 30.0]
+    clips = [synth.make_clip(100 + i, s) for i, s in enumerate(secs)]
+    refs = [O.transcribe_ids(model, c, max_new_tokens=128, keep_logits=True, lm_head_all_rows=False) for c in clips]
+    report["full_b16_min_rel_margin"] = min(_min_rel_margin(r) for r in refs)
+    got = eng.transcribe_ids(clips, max_new_tokens=128)
+    report["full_b16_stage_ms"] = got.stage_ms
+    assert report["full_b16_min_rel_margin"] >= MARGIN_FLOOR_REL
+    for b in range(16):
+        assert got.ids[b] == refs[b].ids, b
+
+
+def test_full_size_1p7b_30s_64_tokens(report):
+    """BASELINE configs[3] model (1.7B dims as recalled in SURVEY.md section 8), one 30 s clip, 64 new tokens, peaked
+    untied head: exact ids on the fused decode step's 1.7B instantiation."""
+    from qwen3_asr_rs_b200 import AsrInference, config_1p7b
+    cfg = O.cfg_1p7b()
+    cfg.text.tie_word_embeddings = False
+    w = synth.make_weights(cfg, 3, peaked_head=True)
+    ecfg = config_1p7b()
+    ecfg.text.tie_word_embeddings = False
+    x = synth.make_clip(7, 30.0)
+    ref = O.transcribe_ids(O.OracleModel(cfg, w), x, max_new_tokens=64, keep_logits=True, lm_head_all_rows=False)
+    report["full1p7b_30s_min_rel_margin"] = _min_rel_margin(ref)
+    eng = AsrInference.from_weights(ecfg, w, device=0)
+    try:
+        got = eng.transcribe_ids([x], max_new_tokens=64)
+        st = eng.stats()
+    finally:
+        eng.close()
+    report["full1p7b_30s_stage_ms"] = got.stage_ms
+    assert report["full1p7b_30s_min_rel_margin"] >= MARGIN_FLOOR_REL
+    assert st["decode_phase_steps"] == 0 and st["gemm_simt_fallbacks"] == 0
+    assert got.ids[0] == ref.ids
+
+
+def test_lossy_f32_matrix_is_rejected(tiny):
+    """Matrices are kept in bf16: an f32 matrix that is not bf16-representable must be an error, not silently
+    different logits (the reference widens everything to f32, weights.rs:74-89)."""
+    import torch
+    from qwen3_asr_rs_b200 import AsrInference, config_tiny
+    from qwen3_asr_rs_b200._lib import AsrbError
+    cfg, w, _ = tiny
+    w2 = dict(w)
+    k = "thinker.model.layers.0.mlp.down_proj.weight"
+    w2[k] = w[k].float() + 1e-4          # no longer representable in bf16
+    with pytest.raises(AsrbError, match="bf16-representable"):
+        AsrInference.from_weights(config_tiny(), w2, device=0)
+    w2[k] = w[k].float()                 # f32 container, bf16-exact values: accepted
+    eng = AsrInference.from_weights(config_tiny(), w2, device=0)
+    eng.close()
+
+
+def test_bad_config_json_is_a_status_not_a_crash(tiny, tmp_path):
+    """config.json with n_window = 0 used to divide by zero inside Dims::derive (SIGFPE)."""
+    import json
+    from qwen3_asr_rs_b200 import AsrInference
+    from qwen3_asr_rs_b200._lib import AsrbError
+    cfg, w, _ = tiny
+    d = tmp_path / "bad"
+    synth.write_checkpoint(str(d), cfg, w)
+    j = json.loads((d / "config.json").read_text())
+    j["thinker_config"]["audio_config"]["n_window"] = 0
+    (d / "config.json").write_text(json.dumps(j))
+    with pytest.raises(AsrbError):
+        AsrInference.load(str(d), device=0)

@@ -20,7 +20,7 @@ for B in [int(a) for a in sys.argv[1:]] or [1, 8, 16]:
     clips = [synth.make_clip(i, 30.0) for i in range(B)]
     row = {"batch": B}
     ids = {}
-    for mode in (("1", "batch") if B > 1 else ()) + (("0", "per_seq"),):
+    for mode in ((("1", "batch"),) if B > 1 else ()) + (("0", "per_seq"),):
         eng.set_option("batch_step", mode[0])
         for _ in range(2):
             r = eng.transcribe_ids(clips, max_new_tokens=NEW)
