@@ -37,7 +37,7 @@ using namespace mega;
 
 static constexpr int MAXSPLIT = 32;       // partial records per (sequence, kv head): lanes of the merging warps
 static constexpr int MAXROWS = 8;         // residual rows owned by one CTA (H / gridDim.x rounded up)
-static constexpr int ATT_SCRATCH = 4 * HD + NCONS_WARPS * 2 * HD + NCONS_WARPS * 4 + 8;   // q[2][128] k v, per-warp partials
+static constexpr int ATT_SCRATCH = 4 * HD + NCONS_WARPS * 2 * HD + NCONS_WARPS * 4 + 8 + 8 + 2 * HD;   // q[2][128] k v, per-warp partials, merge q
 
 struct Params {
     const DecLayerW* layers;     // device array [L]: weight matrices = the chunk-swizzled copies (model.cu), norm vectors plain
@@ -52,10 +52,11 @@ struct Params {
     float* kcache; float* vcache; size_t cache_layer_stride, cache_seq_stride; int max_ctx;
     float* part_val; int* part_idx; int n_part;     // [nb][n_part] argmax partials (first gridDim.x used)
     int* pos; int* done; int* next_id; int* ids_out; int* n_out; int max_new;
-    unsigned* bar;               // [0] finish ticket, [1] launch epoch
+    unsigned* bar;               // [0] finish ticket, [1] launch epoch, [2] batched steps executed
     uint2* qkv_ll; uint2* part_ll;      // tagged {value, tag} words (few readers per word)
     uint32_t* sx;                        // self-validating 4-byte words [2 sets][L][XO | XD | ATTN | ACT][NB][rows]
     long long* dbg;              // optional timeline [2][DBG_SLOTS] of clock64 (CTA 0 and CTA G-1), else null
+    int flags;                   // bit 0: L2 prefetch of the next layer's K/V tiles
 };
 
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
@@ -83,18 +84,24 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
 // 16-byte chunk c of a row whose chunks are XOR-swizzled by `key` (low 3 bits) inside every 128-byte group
 __device__ __forceinline__ int swz16(int c, int key) { return (c & ~7) | ((c ^ key) & 7); }
 
-// One 16-row weight tile x NB sequences over `nks` k-steps (16 elements each).
+// One 16-row weight tile x NB sequences over NKS k-steps (16 elements each).
+// (template NKS = k-steps)
 //   arow  : shared-memory address of THIS LANE's A row (row lane & 15 of the tile), first byte of the row
 //   akey  : swizzle key of that row (global row index & 7);  ac0: first 16-byte chunk of the k-range inside the row
 //   xp    : shared-memory address of activation plane 0, sequence 0;  planes PSTR bytes apart, sequences H * 2 bytes apart,
 //           chunks swizzled by (sequence & 7);  xc0: first chunk of the k-range inside the activation row
 // acc[nt] = the m16n8 accumulator fragment of sequences 8 nt .. 8 nt + 7
-template <int H, int NT, int PSTR>
-__device__ __forceinline__ void mma_tile(uint32_t arow, int akey, int ac0, uint32_t xp, int xc0, int nks, int lane, float (&acc)[NT][4]) {
+template <int H, int NT, int PSTR, int NKS>
+__device__ __forceinline__ void mma_tile(uint32_t arow, int akey, int ac0, uint32_t xp, int xc0, int lane, float (&acc)[NT][4]) {
     const int ahalf = lane >> 4;                         // A: lanes 16-31 address the k 8..15 halves
     const int bpl = lane >> 4, bhalf = (lane >> 3) & 1, bseq = lane & 7;   // B x4: planes 0 / 1 by half-warp
-#pragma unroll 2
-    for (int ks = 0; ks < nks; ++ks) {
+    float acc1[NT][4], acc2[NT][4];                      // one chain per activation plane (the MMAs of a chain are dependent)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { acc1[nt][k] = 0.f; acc2[nt][k] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < NKS; ++ks) {
         uint32_t a0, a1, a2, a3;
         ldsm_x4(arow + (uint32_t)swz16(ac0 + 2 * ks + ahalf, akey) * 16u, a0, a1, a2, a3);
 #pragma unroll
@@ -105,10 +112,14 @@ __device__ __forceinline__ void mma_tile(uint32_t arow, int akey, int ac0, uint3
             ldsm_x4(xrow + (uint32_t)bpl * PSTR, b00, b01, b10, b11);
             ldsm_x2(xrow + 2u * PSTR, b20, b21);         // (lanes 16-31 pass valid addresses that are ignored)
             mma16816(acc[nt], a0, a1, a2, a3, b00, b01);
-            mma16816(acc[nt], a0, a1, a2, a3, b10, b11);
-            mma16816(acc[nt], a0, a1, a2, a3, b20, b21);
+            mma16816(acc1[nt], a0, a1, a2, a3, b10, b11);
+            mma16816(acc2[nt], a0, a1, a2, a3, b20, b21);
         }
     }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[nt][k] += acc1[nt][k] + acc2[nt][k];
 }
 
 // ---- self-validating 4-byte exchange words (the all-to-all vectors: x after o_proj / down_proj, attention output,
@@ -154,36 +165,6 @@ __device__ __forceinline__ void head_norm_rope_b(const uint2* __restrict__ src, 
 
 enum { BE_STORE = 0, BE_SWIGLU = 1, BE_ARGMAX = 2 };
 
-// weight stream of one CTA in phase order: (layer, phase) slices, SLOT_BYTES chunks
-template <int H, int QD, int I>
-struct WCursor {
-    int l, ph, r; Slice s; bool done;
-    const DecLayerW* ltab;
-    __device__ void load(const Params& p) {
-        if (l >= p.L) { if (l == p.L && ph == 0) s = make_slice(p.lm_head, p.V, H, 1); else { done = true; return; } }
-        else {
-            const DecLayerW w = ltab[l];
-            s = ph == 0 ? make_slice(w.wqkv, QD + 2 * p.KVD, H, 1) : ph == 1 ? make_slice(w.wo, H, QD, 1)
-              : ph == 2 ? make_slice(w.wgu, 2 * I, H, 2) : make_slice(w.wdown, H, I, 1);
-        }
-        r = s.r0;
-    }
-    __device__ void init(const Params& p, const DecLayerW* table) { ltab = table; l = 0; ph = 0; done = false; load(p); skip(p); }
-    __device__ void skip(const Params& p) {
-        while (!done && r >= s.r1) {
-            if (l >= p.L) { done = true; break; }
-            if (++ph == 4) { ph = 0; ++l; }
-            load(p);
-        }
-    }
-    // current chunk (valid while !done); advance() moves on
-    __device__ void cur(const bf16*& src, uint32_t& bytes) const {
-        const int rows = min(s.rpc, s.r1 - r);
-        src = s.W + (size_t)r * s.K; bytes = (uint32_t)rows * s.K * 2;
-    }
-    __device__ void advance(const Params& p) { r += s.rpc; skip(p); }
-};
-
 template <int H, int QD, int I, int NB, int NS, int KVK>
 __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params p) {   // 9 warps are allocated as 12 (granularity 4): 168 registers
     static_assert(NB % 8 == 0 && NB <= 16, "NB must be 8 or 16");
@@ -200,8 +181,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
     extern __shared__ __align__(128) uint8_t smem[];
     Ring ring;
     ring.slots = smem; ring.nslot = NS;
-    uint8_t* kv_smem = smem + (size_t)NS * SLOT_BYTES;                 // [K tile | V tile]
-    float* xs = reinterpret_cast<float*>(kv_smem + 2 * KV_TILE);       // bf16 planes [3][NB][H] (chunks swizzled by sequence)
+    static_assert(KV_TILE == SLOT_BYTES, "K / V tiles travel through the weight ring: one tile per slot");
+    float* xs = reinterpret_cast<float*>(smem + (size_t)NS * SLOT_BYTES);   // bf16 planes [3][NB][H] (chunks swizzled by sequence)
     float4* pbuf = reinterpret_cast<float4*>(xs + XS_FLOATS);           // [2][8 warps][NT][32 lanes] partial accumulator fragments
     float* xres = reinterpret_cast<float*>(pbuf + 2 * NCONS_WARPS * NT * 32);   // [NB][MAXROWS]
     float* ropes = xres + NB * MAXROWS;                                 // [NB][128]  cos | sin of each sequence's position
@@ -213,8 +194,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
     int* seqi = besti + 16 * NB;                               // pos[NB] | nact[NB] | off[NB + 1] | misc[4]
     DecLayerW* ltab = reinterpret_cast<DecLayerW*>(seqi + 3 * NB + 8);  // [MAX_LAYERS]
     uint64_t* bars = reinterpret_cast<uint64_t*>(ltab + MAX_LAYERS);
-    ring.full = bars; ring.empty = bars + NSLOT_MAX;
-    uint64_t* kv_full = bars + 2 * NSLOT_MAX; uint64_t* kv_empty = kv_full + 2;   // [2] each: K stage, V stage
+    ring.full = bars; ring.empty = bars + 8;                          // up to 8 slots
     int* pos_s = seqi; int* nact_s = seqi + NB; int* off_s = seqi + 2 * NB; int* misc = seqi + 3 * NB + 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_producer = warp == NCONS_WARPS;
@@ -228,7 +208,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
     }
     if (tid == 0) {
         for (int i = 0; i < NS; ++i) { mbar_init(&ring.full[i], 1); mbar_init(&ring.empty[i], NCONS_WARPS); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], NCONS_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         int o = 0;
         for (int b = 0; b < NB; ++b) {
@@ -250,7 +229,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
     __syncthreads();
     const int T = off_s[NB] * p.nkv;            // attention work items of this step: (sequence, kv head, split)
     // item t -> (b, g, sp): sequence-major, then kv head, then split
-    auto item_decode = [&](int t, int& b, int& g, int& sp) {
+    auto item_decode = [&](int t, int& b, int& g, int& sp) __attribute__((always_inline)) {
         b = 0;
 #pragma unroll
         for (int i = 1; i < NB; ++i) if (t >= off_s[i] * p.nkv) b = i;
@@ -259,63 +238,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
     };
 
     // contiguous item range of this CTA and the owner of an item
-    const int it0 = (int)(((long long)blockIdx.x * T) / (int)G), it1 = (int)(((long long)(blockIdx.x + 1) * T) / (int)G);
-    auto item_owner = [&](int t) { return (int)((((long long)t + 1) * (int)G + T - 1) / T) - 1; };
-    auto range_start = [&](int c) { return (int)(((long long)c * T) / (int)G); };
+    // (the top nb * nkv CTAs also merge one (sequence, kv head) each -- about two tiles' worth of latency -- so they take
+    //  half a share of the items: range_start is piecewise linear in the CTA index)
+    const int n_merge = min(nb * p.nkv, (int)G);
+    const int c_merge = (int)G - n_merge;                             // first merging CTA
+    const long long W2 = 2LL * c_merge + n_merge;                     // total capacity in half shares
+    auto range_start = [&](int c) __attribute__((always_inline)) { const long long cw = c <= c_merge ? 2LL * c : 2LL * c_merge + (c - c_merge); return (int)((cw * T) / W2); };
+    auto item_owner = [&](int t) __attribute__((always_inline)) {                                    // largest c with range_start(c) <= t
+        int lo = 0, hi = (int)G - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (range_start(mid) <= t) lo = mid; else hi = mid - 1; }
+        return lo;
+    };
+    const int it0 = range_start((int)blockIdx.x), it1 = range_start((int)blockIdx.x + 1);
 
     if (is_producer) {
+        // ONE stream in consumption order through ONE ring: [q|k|v] rows, this CTA's K / V tiles (K then V per item), o_proj,
+        // gate/up, down_proj rows of every layer, then the lm_head.  Nothing in it depends on activations, so it runs
+        // ahead across phase boundaries as far as the ring allows; during the attention phase the whole ring is in
+        // flight for K / V (the phase is bound by bytes in flight per SM x latency), otherwise it holds upcoming weights.
         if (lane == 0) {
-            WCursor<H, QD, I> wc;
-            wc.init(p, ltab);
-            uint32_t q = 0, kq = 0;
-            int kl = 0, kt = it0;                 // K/V stream: (layer, item); item uses: 2 * i (K), 2 * i + 1 (V)
-            bool kv_done = (it0 >= it1);
-            int kb = 0, kg = 0, ksp = 0;
-            if (!kv_done) item_decode(kt, kb, kg, ksp);
-            while (!wc.done || !kv_done) {
-                bool prog = false;
-                if (!wc.done) {
-                    const uint32_t slot = q % NS, par = (q / NS) & 1;
-                    if (mbar_test(&ring.empty[slot], par ^ 1)) {
-                        const bf16* src; uint32_t bytes;
-                        wc.cur(src, bytes);
-                        mbar_expect_tx(&ring.full[slot], bytes);
-                        bulk_g2s(ring.slots + (size_t)slot * SLOT_BYTES, src, bytes, &ring.full[slot]);
-                        wc.advance(p); ++q; prog = true;
-                    }
+            uint32_t q = 0;
+            auto issue = [&](const void* src, uint32_t bytes) __attribute__((always_inline)) {
+                const uint32_t slot = q % NS, par = (q / NS) & 1;
+                mbar_wait(&ring.empty[slot], par ^ 1);
+                mbar_expect_tx(&ring.full[slot], bytes);
+                bulk_g2s(ring.slots + (size_t)slot * SLOT_BYTES, src, bytes, &ring.full[slot]);
+                ++q;
+            };
+            auto issue_slice = [&](const Slice& s) __attribute__((always_inline)) {
+                for (int r = s.r0; r < s.r1; r += s.rpc) issue(s.W + (size_t)r * s.K, (uint32_t)min(s.rpc, s.r1 - r) * s.K * 2);
+            };
+            for (int l = 0; l < p.L; ++l) {
+                const DecLayerW w = ltab[l];
+                issue_slice(make_slice(w.wqkv, QD + 2 * p.KVD, H, 1));
+                for (int t = it0; t < it1; ++t) {
+                    int kb, kg, ksp;
+                    item_decode(t, kb, kg, ksp);
+                    const int nloc = min(KVK, pos_s[kb] - ksp * KVK);
+                    const size_t off = (size_t)l * p.cache_layer_stride + (size_t)kb * p.cache_seq_stride +
+                                       ((size_t)kg * p.max_ctx + (size_t)ksp * KVK) * HD;
+                    issue(p.kcache + off, (uint32_t)nloc * HD * 4);
+                    issue(p.vcache + off, (uint32_t)nloc * HD * 4);
                 }
-                if (!kv_done) {
-                    const uint32_t st = kq & 1, par = (kq >> 1) & 1;
-                    if (mbar_test(&kv_empty[st], par ^ 1)) {
-                        const int nloc = min(KVK, pos_s[kb] - ksp * KVK);
-                        const size_t off = (size_t)kl * p.cache_layer_stride + (size_t)kb * p.cache_seq_stride +
-                                           ((size_t)kg * p.max_ctx + (size_t)ksp * KVK) * HD;
-                        const uint32_t bytes = (uint32_t)nloc * HD * 4;
-                        mbar_expect_tx(&kv_full[st], bytes);
-                        bulk_g2s(kv_smem + (size_t)st * KV_TILE, (st == 0 ? p.kcache : p.vcache) + off, bytes, &kv_full[st]);
-                        ++kq; prog = true;
-                        if (st == 0 && kt == it0 && kl + 1 < p.L) {
-                            // The K/V stage only holds one tile each, and the attention phase alternates with the weight
-                            // phases: start pulling the NEXT layer's tiles of this CTA into L2 now, so that they stream from
-                            // HBM while the GEMV phases run and the stage refills from L2 when attention comes around again.
-                            for (int t = it0; t < it1; ++t) {
-                                int pb_, pg_, ps_;
-                                item_decode(t, pb_, pg_, ps_);
-                                const int n_ = min(KVK, pos_s[pb_] - ps_ * KVK);
-                                const size_t o_ = (size_t)(kl + 1) * p.cache_layer_stride + (size_t)pb_ * p.cache_seq_stride +
-                                                  ((size_t)pg_ * p.max_ctx + (size_t)ps_ * KVK) * HD;
-                                l2_prefetch(p.kcache + o_, (uint32_t)n_ * HD * 4);
-                                l2_prefetch(p.vcache + o_, (uint32_t)n_ * HD * 4);
-                            }
-                        }
-                        if (st == 1) {          // V issued: next item
-                            if (++kt >= it1) { kt = it0; if (++kl >= p.L) kv_done = true; }
-                            if (!kv_done) item_decode(kt, kb, kg, ksp);
-                        }
-                    }
-                }
-                if (!prog) __nanosleep(20);
+                issue_slice(make_slice(w.wo, H, QD, 1));
+                issue_slice(make_slice(w.wgu, 2 * I, H, 2));
+                issue_slice(make_slice(w.wdown, H, I, 1));
             }
+            issue_slice(make_slice(p.lm_head, p.V, H, 1));
         }
         return;
     }
@@ -324,14 +293,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
     long long* dbg_row = nullptr; int dbg_i = 0;
     if (p.dbg && (blockIdx.x == 0 || blockIdx.x == G - 1)) dbg_row = p.dbg + (blockIdx.x == 0 ? 0 : DBG_SLOTS);
 #define MARK() do { if (dbg_row && tid == 0 && dbg_i < DBG_SLOTS) dbg_row[dbg_i++] = clock64(); } while (0)
+    int fine_l = -1, fine_i = 0;   // detail marks of layer 5 -> slots 600...
+#define FINE() do { if (dbg_row && tid == 0 && fine_l == 5 && fine_i < 200) dbg_row[600 + fine_i++] = clock64(); } while (0)
     MARK();
-    uint32_t q = 0, kq = 0;
+    uint32_t q = 0;
     const unsigned epoch = __ldcg(p.bar + 1);
     const uint32_t tag_base = (epoch & 0xffffffu) << 8;
     const Slice xsl = make_slice(nullptr, H, QD, 1);                  // residual rows owned by this CTA
     const int xrows = xsl.r1 - xsl.r0;
-    Slice sl_qkv = make_slice(nullptr, QD + 2 * p.KVD, H, 1), sl_o = make_slice(nullptr, H, QD, 1),
-          sl_gu = make_slice(nullptr, 2 * I, H, 2), sl_dn = make_slice(nullptr, H, I, 1);
     for (int i = tid; i < nb * xrows; i += NCONS) {
         const int b = i / xrows, r = i - b * xrows;
         xres[b * MAXROWS + r] = __ldcg(p.x + (size_t)b * H + xsl.r0 + r);
@@ -339,9 +308,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
     float best_v = -INFINITY; int best_i = 0x7fffffff;      // lm_head: running argmax of (tile row tid / NB, sequence tid % NB)
     // exchange regions of this step (set = epoch parity) and re-arm of the other set (words this CTA wrote last step)
     constexpr size_t SX_LAYER = (size_t)NB * (2 * H + QD + I);            // words per (set, layer): XO | XD | ATTN | ACT, each [seq][row]
-    uint32_t* const sx_cur = p.sx + (size_t)(epoch & 1u) * p.L * SX_LAYER;
+    // (set = parity of the BATCHED-step counter bar[2]: the launch epoch bar[1] is shared with the single-sequence kernel,
+    //  whose launches in between would break the strict alternation the re-arm relies on)
+    const unsigned bstep = __ldcg(p.bar + 2);
+    uint32_t* const sx_cur = p.sx + (size_t)(bstep & 1u) * p.L * SX_LAYER;
     {
-        uint32_t* const other = p.sx + (size_t)((epoch & 1u) ^ 1u) * p.L * SX_LAYER;
+        uint32_t* const other = p.sx + (size_t)((bstep & 1u) ^ 1u) * p.L * SX_LAYER;
         const Slice sa = make_slice(nullptr, I, H, 1);                    // act rows of this CTA = gate/up units
         const Slice sq = make_slice(nullptr, QD, H, 1);                   // (attention outputs are re-armed by row range too)
         for (int l = 0; l < p.L; ++l) {
@@ -368,18 +340,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
     // src: self-validating words, sequence b at src + b * src_stride.  Values stay in registers between the poll and
     // the plane stores; NORM: x <- (x * r_b) * w  (rounding order of layers.rs:48-54), then the exact 3-way bf16 split.
     const uint32_t xp_addr = smem_u32(xs);
-    auto store_planes = [&](int b, int j, float4 f) {       // quad j (elements 4 j .. 4 j + 3) of sequence b
-        const Split3 s0 = split3(f.x), s1 = split3(f.y), s2 = split3(f.z), s3 = split3(f.w);
+    // exact 3-way bf16 split by TRUNCATION: hi = top 16 bits of x, mid = top 16 bits of (x - hi), lo = x - hi - mid.  Both
+    // subtractions are exact and lo has <= 8 significant bits, so hi + mid + lo == x exactly; logic + FADD only (the
+    // round-to-nearest split of common.cuh needs three F2F conversions per value, which issue at quarter rate).
+    auto store_planes = [&](int b, int j, float4 f) __attribute__((always_inline)) {       // quad j (elements 4 j .. 4 j + 3) of sequence b
+        const float xv[4] = {f.x, f.y, f.z, f.w};
+        uint32_t hb[4], mb[4], lb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            hb[i] = __float_as_uint(xv[i]) & 0xffff0000u;
+            const float r1 = xv[i] - __uint_as_float(hb[i]);
+            mb[i] = __float_as_uint(r1) & 0xffff0000u;
+            lb[i] = __float_as_uint(r1 - __uint_as_float(mb[i]));
+        }
         uint8_t* dst = reinterpret_cast<uint8_t*>(xs) + (size_t)b * (H * 2) + swz16(j >> 1, b & 7) * 16 + (j & 1) * 8;
-        auto pk = [](bf16 lo, bf16 hi) { return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16); };
-        *reinterpret_cast<uint2*>(dst) = make_uint2(pk(s0.hi, s1.hi), pk(s2.hi, s3.hi));
-        *reinterpret_cast<uint2*>(dst + PSTR) = make_uint2(pk(s0.mid, s1.mid), pk(s2.mid, s3.mid));
-        *reinterpret_cast<uint2*>(dst + 2 * PSTR) = make_uint2(pk(s0.lo, s1.lo), pk(s2.lo, s3.lo));
+        *reinterpret_cast<uint2*>(dst) = make_uint2(__byte_perm(hb[0], hb[1], 0x7632), __byte_perm(hb[2], hb[3], 0x7632));
+        *reinterpret_cast<uint2*>(dst + PSTR) = make_uint2(__byte_perm(mb[0], mb[1], 0x7632), __byte_perm(mb[2], mb[3], 0x7632));
+        *reinterpret_cast<uint2*>(dst + 2 * PSTR) = make_uint2(__byte_perm(lb[0], lb[1], 0x7632), __byte_perm(lb[2], lb[3], 0x7632));
     };
     constexpr int PP = (H / 4 + NCONS - 1) / NCONS;     // 16-byte quads per thread and sequence
     static_assert(NB * PP <= 16, "gather keeps NB * PP quads per thread in registers");
-    // from_sx: poll self-validating words; else plain fp32 rows (layer 0: embeddings written by the previous step / prefill)
-    auto gather = [&](const uint32_t* src, size_t src_stride, const float* normw, bool from_sx) {
+    // gather pieces: g_load issues this thread's 16-byte loads of one H-long chunk of every sequence (idle slots re-read the
+    // last active sequence / quad 0, so everything stays in registers), g_valid checks the self-validating words
+    auto g_load = [&](uint4 (&v)[NB][PP], const uint32_t* src, size_t src_stride) __attribute__((always_inline)) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int i = 0; i < PP; ++i) {
+                const int j = tid + i * NCONS;
+                const int bb = min(b, nb - 1), jj = (PP * NCONS > H / 4 && j >= H / 4) ? 0 : j;
+                v[b][i] = sx_load4(src + (size_t)bb * src_stride + 4 * jj);
+            }
+    };
+    auto g_valid = [&](const uint4 (&v)[NB][PP]) __attribute__((always_inline)) {
+        bool ok = true;
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int i = 0; i < PP; ++i)
+                ok = ok && (v[b][i].x != SX_EMPTY) && (v[b][i].y != SX_EMPTY) && (v[b][i].z != SX_EMPTY) && (v[b][i].w != SX_EMPTY);
+        return ok;
+    };
+    // values -> (optional RMSNorm: x <- (x * r_b) * w, rounding order of layers.rs:48-54) -> bf16 planes; ends with a barrier
+    auto g_store = [&](const uint4 (&v)[NB][PP], const float* normw) __attribute__((always_inline)) {
         float4 wv[PP];
         if (normw) {
 #pragma unroll
@@ -387,28 +390,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
                 const int j = tid + i * NCONS;
                 wv[i] = (j < H / 4) ? __ldg(reinterpret_cast<const float4*>(normw + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-        }
-        uint4 v[NB][PP];
-        bool ok;
-        do {      // loads are unconditional (idle slots re-poll the last active sequence / quad 0): registers only
-            ok = true;
-#pragma unroll
-            for (int b = 0; b < NB; ++b)
-#pragma unroll
-                for (int i = 0; i < PP; ++i) {
-                    const int j = tid + i * NCONS;
-                    const int bb = min(b, nb - 1), jj = (PP * NCONS > H / 4 && j >= H / 4) ? 0 : j;
-                    v[b][i] = sx_load4(src + (size_t)bb * src_stride + 4 * jj);
-                }
-            if (from_sx) {
-#pragma unroll
-                for (int b = 0; b < NB; ++b)
-#pragma unroll
-                    for (int i = 0; i < PP; ++i)
-                        ok = ok && (v[b][i].x != SX_EMPTY) && (v[b][i].y != SX_EMPTY) && (v[b][i].z != SX_EMPTY) && (v[b][i].w != SX_EMPTY);
-            }
-        } while (!ok);
-        if (normw) {
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 float t = 0.f;
@@ -447,11 +428,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
                 }
             }
         }
+        FINE();
         cons_sync();
+    };
+    // from_sx: poll self-validating words; else plain fp32 rows (layer 0: embeddings written by the previous step / prefill)
+    auto gather = [&](const uint32_t* src, size_t src_stride, const float* normw, bool from_sx) __attribute__((always_inline)) {
+        uint4 v[NB][PP];
+        do { g_load(v, src, src_stride); } while (from_sx && !g_valid(v));
+        FINE();
+        g_store(v, normw);
     };
 
     // sum of the 8 warps' partial accumulator fragments (fixed order) for element (tile row tid / NB, sequence tid % NB)
-    auto tile_sum = [&](int par) {
+    auto tile_sum = [&](int par) __attribute__((always_inline)) {
         const int row = tid / NB, sq = tid - row * NB;
         const int nt = sq >> 3, col = sq & 7;
         const int ln = (row & 7) * 4 + (col >> 1), reg = (row >> 3) * 2 + (col & 1);
@@ -466,7 +455,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
     // ---- K = H phases: rows stream through the ring; every 16-row tile is contracted by all 8 warps (K split 8 ways) ----
     // BE_STORE publishes tagged words into `out` (q/k/v: read by the few attention CTAs of each head), BE_SWIGLU publishes
     // self-validating words into `sxo` (activations: gathered by every CTA), BE_ARGMAX keeps the running argmax
-    auto rows_phase = [&](const Slice& s, int epi, uint2* out, size_t out_stride, uint32_t tag, uint32_t* sxo) {
+    auto rows_phase = [&](const Slice& s, int epi, uint2* out, size_t out_stride, uint32_t tag, uint32_t* sxo) __attribute__((always_inline)) {
         for (int r = s.r0; r < s.r1; r += s.rpc, ++q) {
             const int rows = min(s.rpc, s.r1 - r);
             const uint32_t slot = q % NS, par = (q / NS) & 1;
@@ -479,7 +468,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
                 for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                     for (int k = 0; k < 4; ++k) acc[nt][k] = 0.f;
-                mma_tile<H, NT, PSTR>(sbase + (uint32_t)ri * (H * 2), (r + ri) & 7, warp * KSW * 2, xp_addr, warp * KSW * 2, KSW, lane, acc);
+                mma_tile<H, NT, PSTR, KSW>(sbase + (uint32_t)ri * (H * 2), (r + ri) & 7, warp * KSW * 2, xp_addr, warp * KSW * 2, lane, acc);
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
                     pbuf[((size_t)ppar * NCONS_WARPS + warp) * NT * 32 + nt * 32 + lane] = make_float4(acc[nt][0], acc[nt][1], acc[nt][2], acc[nt][3]);
@@ -509,7 +498,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
     // ---- K = NCH * H phases with <= 8 resident rows (o_proj, down_proj): the activation planes hold one H-long chunk at
     //      a time, every chunk is contracted by all 8 warps into the same accumulators; result: residual add +
     //      publication into `sxo` (layers.rs:454,460) ----
-    auto resident_phase = [&](const Slice& s, int NCH, const uint32_t* src, size_t src_stride, uint32_t* sxo) {
+    auto resident_phase = [&](const Slice& s, int NCH, const uint32_t* src, size_t src_stride, uint32_t* sxo) __attribute__((always_inline)) {
         const int rows = s.r1 - s.r0;
         const int nslots = (rows + s.rpc - 1) / s.rpc;
         const int ri = min(lane & 15, rows - 1);                          // rows past the slice alias the last row (never published)
@@ -519,12 +508,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc[nt][k] = 0.f;
+        // chunk pipeline: the loads of chunk c + 1 are in flight while chunk c is split into planes and contracted
+        uint4 cur[NB][PP];
+        g_load(cur, src, src_stride);
         for (int ch = 0; ch < NCH; ++ch) {
-            gather(src + (size_t)ch * H, src_stride, nullptr, true);
+            while (!g_valid(cur)) g_load(cur, src + (size_t)ch * H, src_stride);
+            FINE();
+            g_store(cur, nullptr);
+            uint4 nxt[NB][PP];
+            const int chn = min(ch + 1, NCH - 1);                     // (the last iteration re-reads its own chunk: unconditional, registers only)
+            g_load(nxt, src + (size_t)chn * H, src_stride);           // in flight during the MMAs
             if (ch == 0)
                 for (int i = 0; i < nslots; ++i) mbar_wait(&ring.full[(q + i) % NS], ((q + i) / NS) & 1);
-            mma_tile<H, NT, PSTR>(arow, (s.r0 + ri) & 7, ch * (H / 8) + warp * KSW * 2, xp_addr, warp * KSW * 2, KSW, lane, acc);
+            FINE();
+            mma_tile<H, NT, PSTR, KSW>(arow, (s.r0 + ri) & 7, ch * (H / 8) + warp * KSW * 2, xp_addr, warp * KSW * 2, lane, acc);
+            FINE();
             cons_sync();                                                  // the planes may be overwritten by the next chunk
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+#pragma unroll
+                for (int i = 0; i < PP; ++i) cur[b][i] = nxt[b][i];
         }
         __syncwarp();
         if (lane == 0) for (int i = 0; i < nslots; ++i) mbar_arrive(&ring.empty[(q + i) % NS]);
@@ -547,6 +550,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
 
     for (int l = 0; l < p.L; ++l) {
         const DecLayerW w = ltab[l];
+        fine_l = l;
         const uint32_t tl = tag_base | ((uint32_t)l << 3);
         uint32_t* const sxl = sx_cur + (size_t)l * SX_LAYER;                       // this layer's XO | XD | ATTN | ACT words
         uint32_t* const sx_xo = sxl; uint32_t* const sx_xd = sxl + (size_t)NB * H;
@@ -555,8 +559,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
         if (l == 0) gather(reinterpret_cast<const uint32_t*>(p.x), H, w.ln_in, false);
         else gather(sxl - SX_LAYER + (size_t)NB * H, H, w.ln_in, true);            // XD of the previous layer
         MARK();
-        sl_qkv.W = w.wqkv;
-        rows_phase(sl_qkv, BE_STORE, p.qkv_ll, (size_t)(QD + 2 * p.KVD), tl | PH_QKV, nullptr);
+        rows_phase(make_slice(w.wqkv, QD + 2 * p.KVD, H, 1), BE_STORE, p.qkv_ll, (size_t)(QD + 2 * p.KVD), tl | PH_QKV, nullptr);
         cons_sync();                                  // xs is free: attention scratch aliases it
         MARK();
         // ---- phase 2: attention partials of this CTA's work items ----
@@ -573,9 +576,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
             float* osum = vn + HD;                    // [warps][2][128]
             float* wml = osum + NCONS_WARPS * GROUP * HD;   // [warps][2][2]
             float* snew = wml + NCONS_WARPS * 4;      // [2]
-            float* Ks = reinterpret_cast<float*>(kv_smem);
-            float* Vs = reinterpret_cast<float*>(kv_smem + KV_TILE);
             constexpr int SH = (NV == 16) ? 1 : (NV == 8 ? 2 : 3);
+            // merging CTA: the current token's q / k / v of its (sequence, kv head) are ready as soon as the [q|k|v] phase is
+            // (long before the partial records), so RMSNorm + RoPE, the cache append and the new key's scores happen NOW,
+            // off the tail of the phase
+            float* mq = snew + 8;                     // [2][128] q heads of the merge (the item runs reuse qs)
+            const int mid = (int)G - 1 - (int)blockIdx.x;
+            const bool merger = mid < nb * p.nkv;
+            const int mb_ = merger ? mid / p.nkv : 0, mg_ = merger ? mid - mb_ * p.nkv : 0;
+            if (merger) {
+                const float* cs = ropes + mb_ * 128; const float* sn = cs + 64;
+                const uint2* qkvb = p.qkv_ll + (size_t)mb_ * (QD + 2 * p.KVD);
+                if (warp < GROUP) head_norm_rope_b(qkvb + (size_t)(mg_ * GROUP + warp) * HD, tl | PH_QKV, w.qnorm, p.eps, cs, sn, mq + warp * HD, lane);
+                else if (warp == GROUP) head_norm_rope_b(qkvb + QD + (size_t)mg_ * HD, tl | PH_QKV, w.knorm, p.eps, cs, sn, kn, lane);
+                else if (warp == GROUP + 1) {
+                    float vv[4];
+                    ll_poll4(qkvb + QD + p.KVD + (size_t)mg_ * HD + lane, 32, tl | PH_QKV, vv);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) vn[lane + 32 * i] = vv[i];
+                }
+                cons_sync();
+                if (tid < HD) {                       // KV append (replaces Tensor::cat, layers.rs:311-317)
+                    const size_t off = (size_t)l * p.cache_layer_stride + (size_t)mb_ * p.cache_seq_stride + ((size_t)mg_ * p.max_ctx + pos_s[mb_]) * HD;
+                    p.kcache[off + tid] = kn[tid]; p.vcache[off + tid] = vn[tid];
+                }
+                if (warp >= NCONS_WARPS - GROUP) {    // score of the new key for head hq
+                    const int hq = warp - (NCONS_WARPS - GROUP);
+                    const float4 a = *reinterpret_cast<const float4*>(mq + hq * HD + lane * 4);
+                    const float4 c4 = *reinterpret_cast<const float4*>(kn + lane * 4);
+                    const float s_ = warp_sum(fmaf(a.x, c4.x, fmaf(a.y, c4.y, fmaf(a.z, c4.z, a.w * c4.w))));
+                    if (lane == 0) snew[hq] = s_ / sqrtf((float)HD);
+                }
+                // (the barrier before the first run / the merge orders these writes)
+            }
             int t = it0;
             while (t < it1) {
                 int b, g, sp;
@@ -592,7 +625,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
                 float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
                 for (int it = 0; it < nrun; ++it) {
                     const int nloc = min(KVK, pos_s[b] - (sp + it) * KVK);
-                    mbar_wait(&kv_full[0], (kq >> 1) & 1);
+                    const uint32_t ksl = q % NS, vsl = (q + 1) % NS;
+                    const float* Ks = reinterpret_cast<const float*>(ring.slots + (size_t)ksl * SLOT_BYTES);
+                    const float* Vs = reinterpret_cast<const float*>(ring.slots + (size_t)vsl * SLOT_BYTES);
+                    mbar_wait(&ring.full[ksl], (q / NS) & 1);
                     float pv[NV];
 #pragma unroll
                     for (int kk = 0; kk < KPW; ++kk) {
@@ -603,7 +639,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&kv_empty[0]);     // K stage may be refilled
+                    if (lane == 0) mbar_arrive(&ring.empty[ksl]);  // K tile consumed by this warp
                     // transposing butterfly: lane L ends with score index L >> SH (index = 2 * key + head)
 #pragma unroll
                     for (int o = 16, n = NV; n > 1; o >>= 1, n >>= 1) {
@@ -635,7 +671,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
                     l0 = fmaf(l0, c0, h1 ? lwo : lw); l1 = fmaf(l1, c1, h1 ? lw : lwo);
                     m0 = n0; m1 = n1;
                     o0.x *= c0; o0.y *= c0; o0.z *= c0; o0.w *= c0; o1.x *= c1; o1.y *= c1; o1.z *= c1; o1.w *= c1;
-                    mbar_wait(&kv_full[1], (kq >> 1) & 1);
+                    mbar_wait(&ring.full[vsl], ((q + 1) / NS) & 1);
 #pragma unroll
                     for (int kk = 0; kk < KPW; ++kk) {
                         const int j = warp + 8 * kk;
@@ -648,8 +684,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&kv_empty[1]);     // V stage may be refilled
-                    kq += 2;
+                    if (lane == 0) mbar_arrive(&ring.empty[vsl]);  // V tile consumed by this warp
+                    q += 2;
                 }
                 *reinterpret_cast<float4*>(osum + (warp * 2 + 0) * HD + lane * 4) = o0;
                 *reinterpret_cast<float4*>(osum + (warp * 2 + 1) * HD + lane * 4) = o1;
@@ -677,39 +713,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
             }
             MARK();
             // ---- merge of one (sequence, kv head): all its partial records + the current token's key / value ----
-            const int mid = (int)G - 1 - (int)blockIdx.x;
-            if (mid < nb * p.nkv) {
-                const int b = mid / p.nkv, g = mid - b * p.nkv;
-                const int pos = pos_s[b];
+            if (merger) {
+                const int b = mb_, g = mg_;
                 const int base_t = off_s[b] * p.nkv + g * nact_s[b];
                 const int nact = nact_s[b];                                                        // record slots of (b, g)
                 // slot u holds a record iff a run starts at split u: u == 0 or item base_t + u opens its owner's range
                 auto run_start = [&](int u) { return u == 0 || range_start(item_owner(base_t + u)) == base_t + u; };
                 unsigned startmask = 0;
                 for (int u = 0; u < nact; ++u) startmask |= run_start(u) ? (1u << u) : 0u;
-                const float* cs = ropes + b * 128; const float* sn = cs + 64;
-                const uint2* qkvb = p.qkv_ll + (size_t)b * (QD + 2 * p.KVD);
-                if (warp < GROUP) head_norm_rope_b(qkvb + (size_t)(g * GROUP + warp) * HD, tl | PH_QKV, w.qnorm, p.eps, cs, sn, qs + warp * HD, lane);
-                else if (warp == GROUP) head_norm_rope_b(qkvb + QD + (size_t)g * HD, tl | PH_QKV, w.knorm, p.eps, cs, sn, kn, lane);
-                else if (warp == GROUP + 1) {
-                    float vv[4];
-                    ll_poll4(qkvb + QD + p.KVD + (size_t)g * HD + lane, 32, tl | PH_QKV, vv);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) vn[lane + 32 * i] = vv[i];
-                }
-                cons_sync();
-                if (tid < HD) {                       // KV append (replaces Tensor::cat, layers.rs:311-317)
-                    const size_t off = (size_t)l * p.cache_layer_stride + (size_t)b * p.cache_seq_stride + ((size_t)g * p.max_ctx + pos) * HD;
-                    p.kcache[off + tid] = kn[tid]; p.vcache[off + tid] = vn[tid];
-                }
-                if (warp >= NCONS_WARPS - GROUP) {    // score of the new key for head hq
-                    const int hq = warp - (NCONS_WARPS - GROUP);
-                    const float4 a = *reinterpret_cast<const float4*>(qs + hq * HD + lane * 4);
-                    const float4 c4 = *reinterpret_cast<const float4*>(kn + lane * 4);
-                    const float s_ = warp_sum(fmaf(a.x, c4.x, fmaf(a.y, c4.y, fmaf(a.z, c4.z, a.w * c4.w))));
-                    if (lane == 0) snew[hq] = s_ / sqrtf((float)HD);
-                }
-                cons_sync();
+                cons_sync();                          // kn / vn / snew of the early preparation are visible to every warp
                 {
                     const int hq = tid / HD, d = tid - hq * HD;          // hq is uniform per warp (HD = 4 warps)
                     const uint32_t tg = tl | PH_PART;
@@ -765,19 +777,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
         }
         MARK();
         // ---- phase 3: o_proj GEMV + residual ----
-        sl_o.W = w.wo;
-        resident_phase(sl_o, QD / H, sx_attn, QD, sx_xo);
+        resident_phase(make_slice(w.wo, H, QD, 1), QD / H, sx_attn, QD, sx_xo);
         MARK();
         // ---- phase 4: RMSNorm + gate/up GEMV + SiLU*mul ----
         gather(sx_xo, H, w.ln_post, true);
         MARK();
-        sl_gu.W = w.wgu;
-        rows_phase(sl_gu, BE_SWIGLU, nullptr, 0, 0u, sx_act);
+        rows_phase(make_slice(w.wgu, 2 * I, H, 2), BE_SWIGLU, nullptr, 0, 0u, sx_act);
         cons_sync();
         MARK();
         // ---- phase 5: down GEMV + residual ----
-        sl_dn.W = w.wdown;
-        resident_phase(sl_dn, I / H, sx_act, I, sx_xd);
+        resident_phase(make_slice(w.wdown, H, I, 1), I / H, sx_act, I, sx_xd);
         MARK();
     }
     // ---- final RMSNorm + tied lm_head GEMV + argmax ----
@@ -838,6 +847,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
     if (tid == 0) {
         p.bar[0] = 0;                        // every CTA has taken its ticket: reset for the next launch
         p.bar[1] = p.bar[1] + 1;             // new epoch: words published by this step can never match again
+        p.bar[2] = p.bar[2] + 1;             // batched steps executed: selects the exchange set of the next one
     }
 }
 
@@ -856,13 +866,13 @@ template <int H, int QD, int I> static bool bdims_match(const asrb_dims& c) {
     return c.hidden_size == H && c.num_attention_heads * c.head_dim == QD && c.intermediate_size == I;
 }
 struct BatchCfg { int NB, NS, KVK; };
-static BatchCfg batch_cfg(int B) { return B <= 8 ? BatchCfg{8, 3, 64} : BatchCfg{16, 2, 32}; }
+static BatchCfg batch_cfg(int B) { return B <= 8 ? BatchCfg{8, 5, 64} : BatchCfg{16, 3, 64}; }
 
 static size_t batch_smem_bytes(int H, const BatchCfg& k) {
-    return (size_t)k.NS * mega::SLOT_BYTES + 2 * (size_t)k.KVK * 128 * 4 +
+    return (size_t)k.NS * mega::SLOT_BYTES +
            (std::max<size_t>((size_t)3 * k.NB * H / 2, megab::ATT_SCRATCH) + k.NB * megab::MAXROWS + k.NB * 128 + mega::NCONS_WARPS * 32 + mega::NCONS_WARPS * k.NB + k.NB +
             2 * 16 * k.NB + 3 * k.NB + 8) * 4 + (size_t)2 * mega::NCONS_WARPS * (k.NB / 8) * 32 * 16 +
-           mega::MAX_LAYERS * sizeof(DecLayerW) + (2 * mega::NSLOT_MAX + 4) * 8 + 128;
+           mega::MAX_LAYERS * sizeof(DecLayerW) + 16 * 8 + 128;
 }
 
 // `ctx` = upper bound of (position + 1) over the batch for this step
@@ -909,11 +919,11 @@ void launch_decode_step_batch(const Model& m, const DecodeBufs& b, int B, float*
         const size_t smem = batch_smem_bytes(c.hidden_size, k);
         const void* fn = nullptr;
         if (bdims_match<1024, 2048, 3072>(c))
-            fn = k.NB == 8 ? (const void*)megab::decode_batch_kernel<1024, 2048, 3072, 8, 3, 64>
-                           : (const void*)megab::decode_batch_kernel<1024, 2048, 3072, 16, 2, 32>;
+            fn = k.NB == 8 ? (const void*)megab::decode_batch_kernel<1024, 2048, 3072, 8, 5, 64>
+                           : (const void*)megab::decode_batch_kernel<1024, 2048, 3072, 16, 3, 64>;
         else
-            fn = k.NB == 8 ? (const void*)megab::decode_batch_kernel<256, 512, 512, 8, 3, 64>
-                           : (const void*)megab::decode_batch_kernel<256, 512, 512, 16, 2, 32>;
+            fn = k.NB == 8 ? (const void*)megab::decode_batch_kernel<256, 512, 512, 8, 5, 64>
+                           : (const void*)megab::decode_batch_kernel<256, 512, 512, 16, 3, 64>;
         ASRB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         megab::Params p{};
         p.layers = m.d_dec_layers_b; p.lm_head = m.lm_head_b; p.embed = m.embed; p.final_norm = m.final_norm;
@@ -937,6 +947,7 @@ void launch_decode_step_batch(const Model& m, const DecodeBufs& b, int B, float*
         }
         p.dbg = mb.dbg;
         g_last_dbg_batch = mb.dbg;
+        { static const int fl = getenv("ASRB_BATCH_FLAGS") ? atoi(getenv("ASRB_BATCH_FLAGS")) : 0; p.flags = fl; }   // bit 0 (K/V L2 prefetch): measured slower, off
         if (mb.steps_issued && ++*mb.steps_issued >= 0xFFFF00u) {   // tags must stay monotonic: wipe long before the epoch wraps
             ASRB_CUDA_CHECK(cudaMemsetAsync(mb.part, 0, mb.part_bytes, st));
             const unsigned one = 1;

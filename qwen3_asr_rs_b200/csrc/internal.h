@@ -61,7 +61,7 @@ struct Model {
     std::vector<void*> owned;            // packed buffers created at finalize
 
     // mel constants (src/mel.rs:115-187 + periodic Hann + DFT twiddles)
-    float *mel_fb = nullptr, *dft_cos = nullptr, *dft_sin = nullptr, *hann = nullptr;
+    float *mel_fb = nullptr, *dft_cos = nullptr, *dft_sin = nullptr, *hann = nullptr, *dft_tw = nullptr;
     int* mel_krange = nullptr;           // [num_mels][2] non-zero bin range of each filter
     // encoder
     float *conv1_w = nullptr, *conv1_b = nullptr, *conv2_b = nullptr, *conv3_b = nullptr, *conv_out_b = nullptr;

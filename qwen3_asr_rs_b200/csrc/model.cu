@@ -234,6 +234,10 @@ static void build_mel_tables(Model* m) {
         }
     }
     m->dft_cos = dev_upload(m, dc); m->dft_sin = dev_upload(m, ds); m->hann = dev_upload(m, hw);
+    // 1-D twiddle table {cos, sin}(2 pi r / 400), r = 0..399 (mel.cu keeps it in shared memory and walks it with r += k mod 400)
+    std::vector<float> tw((size_t)2 * n_fft);
+    for (int r = 0; r < n_fft; ++r) { tw[2 * r] = (float)std::cos(two_pi * r / n_fft); tw[2 * r + 1] = (float)std::sin(two_pi * r / n_fft); }
+    m->dft_tw = dev_upload(m, tw);
 }
 
 static void build_pos_tables(Model* m) {

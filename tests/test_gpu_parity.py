@@ -347,9 +347,11 @@ def test_batch_step_tiny(tiny, tiny_engine, secs):
     n_new = 14
     try:
         tiny_engine.set_option("batch_step", "1")
-        before = tiny_engine.stats().get("decode_batch_steps", 0)
-        got = tiny_engine.transcribe_ids(clips, max_new_tokens=n_new).ids
-        assert tiny_engine.stats()["decode_batch_steps"] == before + n_new - 1      # the batched kernel really ran
+        got = tiny_engine.transcribe_ids(clips, max_new_tokens=n_new)
+        assert got.decode_steps == n_new - 1
+        st = tiny_engine.stats()              # (counters restart when the engine re-creates its session for a larger batch)
+        assert st["decode_batch_steps"] >= n_new - 1 and st["decode_phase_steps"] == 0      # the batched kernel really ran
+        got = got.ids
         tiny_engine.set_option("batch_step", "0")
         per_seq = tiny_engine.transcribe_ids(clips, max_new_tokens=n_new).ids
     finally:
@@ -402,7 +404,9 @@ def test_full_size_0p6b_batch8_30s_128_tokens(full_peaked, report):
     """north_star shape: Qwen3-ASR-0.6B, batch 8 x 30 s, 128 new tokens per clip -- exact ids for every clip through the
     batch-aware fused decode step (and the batch-8 encoder / prefill GEMMs), logits within tolerance."""
     model, eng = full_peaked
-    clips = [synth.make_clip(i, 30.0) for i in range(8)]
+    # clips whose oracle-side worst top-1/top-2 gap is >= 5e-4 of max|logit| (scanned on the CPU; clips 0, 2, 5, 9 ... sit
+    # at 1e-4 .. 6e-7, i.e. inside summation-order noise, where "exact ids" is a coin toss for any implementation)
+    clips = [synth.make_clip(i, 30.0) for i in (1, 3, 4, 6, 7, 8, 10, 17)]
     refs = [O.transcribe_ids(model, c, max_new_tokens=128, keep_logits=True, lm_head_all_rows=False) for c in clips]
     report["full_b8_min_rel_margin"] = min(_min_rel_margin(r) for r in refs)
     eng.mel(clips)
@@ -413,7 +417,7 @@ def test_full_size_0p6b_batch8_30s_128_tokens(full_peaked, report):
     got = eng.transcribe_ids(clips, max_new_tokens=128)
     st = eng.stats()
     report["full_b8_stage_ms"] = got.stage_ms
-    assert report["full_b8_min_rel_margin"] >= MARGIN_FLOOR_REL
+    assert report["full_b8_min_rel_margin"] >= 5 * MARGIN_FLOOR_REL
     assert report["full_b8_prefill_logits_rel_err"] <= LOGIT_RTOL
     assert st["decode_batch_steps"] == before + 127 and st["gemm_simt_fallbacks"] == 0
     for b in range(8):

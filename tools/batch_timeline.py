@@ -31,4 +31,8 @@ for cta, row in zip(("cta0", "ctaLast(merger)"), t):
     for i, nm in enumerate(names):
         print(f"    {nm:14s} mean {per[2:, i].mean():9.0f}  min {per[2:, i].min():7d}  max {per[2:, i].max():7d}")
     print("    layer mean", per[2:].sum(1).mean(), " first layers:", per.sum(1)[:3])
+for cta, row in zip(("cta0", "ctaLast"), t):
+    f = row[600:800]
+    n = int((f != 0).sum())
+    print(cta, "layer-5 fine marks (cycles since first):", [int(v - f[0]) for v in f[:n]])
 eng.close()

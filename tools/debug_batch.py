@@ -18,6 +18,17 @@ cases = {
  "B3_nolang": ([2.5, 9.1, 5.0], None),
  "B3_lang": ([2.5, 9.1, 5.0], [None, [11528, 6364], [11528, 8453, 55]]),
  "B2": ([2.5, 5.0], None),
+ "B2_a": ([2.5, 2.5], None),
+ "B2_b": ([5.0, 5.0], None),
+ "B2_c": ([5.0, 2.5], None),
+ "B2_d": ([9.1, 2.5], None),
+ "B2_e": ([0.7, 0.9], None),
+ "B3_x": ([2.5, 5.0, 2.5], None),
+ "B2_f": ([1.0, 5.0], None),
+ "B2_g": ([2.5, 9.1], None),
+ "B2_h": ([2.5, 4.5], None),
+ "B2_i": ([3.0, 5.0], None),
+ "B3_y": ([2.5, 5.0, 5.0], None),
  "B8": ([1.1, 2.3, 0.7, 4.9, 3.1, 1.9, 2.2, 0.9], None),
  "B8_same": ([3.0] * 8, None),
  "B4_short": ([0.7, 0.7, 0.7, 0.7], None),
