@@ -294,6 +294,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
     if (p.dbg && (blockIdx.x == 0 || blockIdx.x == G - 1)) dbg_row = p.dbg + (blockIdx.x == 0 ? 0 : DBG_SLOTS);
 #define MARK() do { if (dbg_row && tid == 0 && dbg_i < DBG_SLOTS) dbg_row[dbg_i++] = clock64(); } while (0)
     int fine_l = -1, fine_i = 0;   // detail marks of layer 5 -> slots 600...
+// every CTA: wall clock (globaltimer, ns) of event k of layer 5 -> slots [2048 + 8 * cta + k)
+#define GT(k) do { if (p.dbg && tid == 0 && fine_l == 5) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg[2 * DBG_SLOTS + 8 * blockIdx.x + (k)] = (long long)t_; } } while (0)
 #define FINE() do { if (dbg_row && tid == 0 && fine_l == 5 && fine_i < 200) dbg_row[600 + fine_i++] = clock64(); } while (0)
     MARK();
     uint32_t q = 0;
@@ -559,9 +561,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
         if (l == 0) gather(reinterpret_cast<const uint32_t*>(p.x), H, w.ln_in, false);
         else gather(sxl - SX_LAYER + (size_t)NB * H, H, w.ln_in, true);            // XD of the previous layer
         MARK();
+        GT(0);
         rows_phase(make_slice(w.wqkv, QD + 2 * p.KVD, H, 1), BE_STORE, p.qkv_ll, (size_t)(QD + 2 * p.KVD), tl | PH_QKV, nullptr);
         cons_sync();                                  // xs is free: attention scratch aliases it
         MARK();
+        GT(1);
         // ---- phase 2: attention partials of this CTA's work items ----
         // Items are sorted (sequence, kv head, split) and dealt in CONTIGUOUS ranges: a CTA's range consists of a few
         // "runs" of consecutive splits of one (sequence, kv head).  Within a run every warp keeps an online-softmax
@@ -712,6 +716,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
                 t += nrun;
             }
             MARK();
+            GT(2);
             // ---- merge of one (sequence, kv head): all its partial records + the current token's key / value ----
             if (merger) {
                 const int b = mb_, g = mg_;
@@ -776,15 +781,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
             }
         }
         MARK();
+        GT(3);
         // ---- phase 3: o_proj GEMV + residual ----
         resident_phase(make_slice(w.wo, H, QD, 1), QD / H, sx_attn, QD, sx_xo);
         MARK();
+        GT(4);
         // ---- phase 4: RMSNorm + gate/up GEMV + SiLU*mul ----
         gather(sx_xo, H, w.ln_post, true);
         MARK();
         rows_phase(make_slice(w.wgu, 2 * I, H, 2), BE_SWIGLU, nullptr, 0, 0u, sx_act);
         cons_sync();
         MARK();
+        GT(5);
         // ---- phase 5: down GEMV + residual ----
         resident_phase(make_slice(w.wdown, H, I, 1), I / H, sx_act, I, sx_xd);
         MARK();
@@ -856,9 +864,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
 // host side ---------------------------------------------------------------------------------------
 static long long* g_last_dbg_batch = nullptr;   // debug only (ASRB_MEGA_DEBUG): timeline buffer of the last batched launch
 int decode_batch_debug_timeline(long long* out, int cap) {
-    if (!g_last_dbg_batch || cap < 2 * mega::DBG_SLOTS) return 0;
+    if (!g_last_dbg_batch || cap < 4 * mega::DBG_SLOTS) return 0;
     cudaDeviceSynchronize();
-    cudaMemcpy(out, g_last_dbg_batch, 2 * mega::DBG_SLOTS * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(out, g_last_dbg_batch, 4 * mega::DBG_SLOTS * sizeof(long long), cudaMemcpyDeviceToHost);
     return mega::DBG_SLOTS;
 }
 

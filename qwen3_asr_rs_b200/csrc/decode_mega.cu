@@ -894,6 +894,6 @@ int decode_mega_debug_timeline(long long* out, int cap) {
     cudaMemcpy(out, g_last_dbg, 2 * mega::DBG_SLOTS * sizeof(long long), cudaMemcpyDeviceToHost);
     return mega::DBG_SLOTS;
 }
-int decode_mega_dbg_slots() { return 2 * mega::DBG_SLOTS; }
+int decode_mega_dbg_slots() { return 4 * mega::DBG_SLOTS; }   // [0, 2048): two CTA timelines; [2048, 4096): per-CTA wall-clock table (decode_batch.cu)
 
 }  // namespace asrb

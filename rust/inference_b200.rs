@@ -18,7 +18,7 @@ mod b200_arm {
         /// `src/inference.rs:30-86`; the device pick of `src/main.rs:51-58` becomes the `device` ordinal.
         pub fn load(model_dir: &str, device: i32) -> Result<Self> {
             let tokenizer = AsrTokenizer::from_dir(model_dir)?;                      // unchanged (:76-84)
-            let engine = B200Engine::load(model_dir, device, 30 * 60, 4096)?;        // cap 4096 new tokens (:153)
+            let engine = B200Engine::load(model_dir, device, 4096)?;                 // cap 4096 new tokens (:153); session sized per clip
             Ok(Self { engine, tokenizer })
         }
 

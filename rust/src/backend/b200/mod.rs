@@ -21,9 +21,11 @@ struct Session(*mut ffi::asrb_session);
 impl Drop for Session { fn drop(&mut self) { unsafe { ffi::asrb_session_free(self.0); } } }
 
 /// Device context + immutable weights + one session (KV cache, scratch, stream) for batch-1 `transcribe()` calls.
+/// The session is created lazily and re-created only when a clip is longer than its capacity (the reference handles
+/// arbitrary-length audio; a session sized for the worst case up front would pin ~1 GB of scratch per minute of audio).
 /// Field order = drop order: session before model before context.
 pub struct B200Engine {
-    session: Session,
+    session: std::cell::RefCell<Option<(Session, usize)>>,   // (handle, capacity in samples)
     model: Model,
     _ctx: Ctx,
     max_new_tokens: usize,
@@ -35,8 +37,8 @@ unsafe impl Send for B200Engine {}
 
 impl B200Engine {
     /// Replaces the loaders of `AsrInference::load` (`src/inference.rs:39-74`): config.json + safetensors (single or
-    /// sharded) are read by the library, bf16 stays bf16.  `max_seconds` bounds the audio length of one call.
-    pub fn load(model_dir: &str, device: i32, max_seconds: usize, max_new_tokens: usize) -> Result<Self> {
+    /// sharded) are read by the library, bf16 stays bf16.
+    pub fn load(model_dir: &str, device: i32, max_new_tokens: usize) -> Result<Self> {
         let mut ctx = ptr::null_mut();
         check(unsafe { ffi::asrb_init(device, &mut ctx) })?;
         let ctx = Ctx(ctx);
@@ -44,9 +46,21 @@ impl B200Engine {
         let mut model = ptr::null_mut();
         check(unsafe { ffi::asrb_model_load(ctx.0, dir.as_ptr(), &mut model) })?;
         let model = Model(model);
+        Ok(Self { session: std::cell::RefCell::new(None), model, _ctx: ctx, max_new_tokens })
+    }
+
+    /// Session with room for `n_samples`: capacity grows in 30 s steps, the old session is dropped first.
+    fn session_for(&self, n_samples: usize) -> Result<*mut ffi::asrb_session> {
+        let mut slot = self.session.borrow_mut();
+        if let Some((s, cap)) = slot.as_ref() {
+            if *cap >= n_samples { return Ok(s.0); }
+        }
+        *slot = None;
+        let cap = ((n_samples + 479_999) / 480_000).max(1) * 480_000;
         let mut session = ptr::null_mut();
-        check(unsafe { ffi::asrb_session_create(model.0, 1, (16_000 * max_seconds) as i64, 16, max_new_tokens as i32, &mut session) })?;
-        Ok(Self { session: Session(session), model, _ctx: ctx, max_new_tokens })
+        check(unsafe { ffi::asrb_session_create(self.model.0, 1, cap as i64, 16, self.max_new_tokens as i32, &mut session) })?;
+        *slot = Some((Session(session), cap));
+        Ok(session)
     }
 
     pub fn dims(&self) -> Result<ffi::AsrbDims> {
@@ -64,8 +78,9 @@ impl B200Engine {
         let sl = [samples.len() as i64];
         let lp = [lang_ids.map_or(ptr::null(), |v| v.as_ptr())];
         let ll = [lang_ids.map_or(0, |v| v.len() as i32)];
+        let session = self.session_for(samples.len())?;
         check(unsafe {
-            ffi::asrb_transcribe_ids(self.session.0, sp.as_ptr(), sl.as_ptr(), 1, lp.as_ptr(), ll.as_ptr(),
+            ffi::asrb_transcribe_ids(session, sp.as_ptr(), sl.as_ptr(), 1, lp.as_ptr(), ll.as_ptr(),
                                      self.max_new_tokens as i32, ids.as_mut_ptr(), &mut n)
         })?;
         Ok(ids[..n as usize].iter().map(|&t| t as i64).collect())

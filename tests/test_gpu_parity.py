@@ -347,10 +347,14 @@ def test_batch_step_tiny(tiny, tiny_engine, secs):
     n_new = 14
     try:
         tiny_engine.set_option("batch_step", "1")
+        before = tiny_engine.stats()
         got = tiny_engine.transcribe_ids(clips, max_new_tokens=n_new)
         assert got.decode_steps == n_new - 1
         st = tiny_engine.stats()              # (counters restart when the engine re-creates its session for a larger batch)
-        assert st["decode_batch_steps"] >= n_new - 1 and st["decode_phase_steps"] == 0      # the batched kernel really ran
+        fresh = st["decode_batch_steps"] < before.get("decode_batch_steps", 0) + n_new - 1
+        base = {} if fresh else before
+        assert st["decode_batch_steps"] - base.get("decode_batch_steps", 0) == n_new - 1      # the batched kernel really ran
+        assert st["decode_phase_steps"] - base.get("decode_phase_steps", 0) == 0
         got = got.ids
         tiny_engine.set_option("batch_step", "0")
         per_seq = tiny_engine.transcribe_ids(clips, max_new_tokens=n_new).ids
@@ -373,10 +377,11 @@ def test_peaked_untied_head_tiny(report):
     ecfg.text.tie_word_embeddings = False
     eng = AsrInference.from_weights(ecfg, w, device=0)
     try:
-        clips = [synth.make_clip(500 + i, s) for i, s in enumerate([4.0, 12.3, 0.8, 7.7, 2.2])]
+        # clips picked by their oracle-side worst gap (>= 1.3e-3 of max|logit|; 502 / 504 sit at 2e-5 / 1.4e-4)
+        clips = [synth.make_clip(i, s) for i, s in [(500, 4.0), (501, 12.3), (507, 1.5), (503, 7.7), (505, 4.0)]]
         refs = [O.transcribe_ids(model, c, max_new_tokens=40, keep_logits=True) for c in clips]
         report["peaked_tiny_min_rel_margin"] = min(_min_rel_margin(r) for r in refs)
-        assert report["peaked_tiny_min_rel_margin"] >= MARGIN_FLOOR_REL
+        assert report["peaked_tiny_min_rel_margin"] >= 10 * MARGIN_FLOOR_REL
         assert eng.transcribe_ids(clips[:1], max_new_tokens=40).ids[0] == refs[0].ids
         got = eng.transcribe_ids(clips, max_new_tokens=40).ids
         for g, r in zip(got, refs):
@@ -426,16 +431,19 @@ def test_full_size_0p6b_batch8_30s_128_tokens(full_peaked, report):
 
 def test_full_size_0p6b_16_sequences_512_token_kv(full_peaked, report):
     """BASELINE configs[4] per GPU: 16 sequences decoding around a 512-token KV cache (prompts of 300..405 tokens +
-    128 new tokens cross 512 for the long ones), ragged lengths -- exact ids for every sequence (NB = 16 instantiation,
+    128 new tokens cross 512 for the 30 s ones), ragged lengths -- exact ids for every sequence (NB = 16 instantiation,
     32-key attention splits, up to 17 splits per kv head)."""
     model, eng = full_peaked
-    secs = [30.0, 22.6, 27.7, 30.0, 24.1, 29.2, 30.0, 21.3, 26.4, 30.0, 28.8, 23.5, 30.0, 25.9, 29.9, 30.0]
-    clips = [synth.make_clip(100 + i, s) for i, s in enumerate(secs)]
+    # (clip index, seconds): ragged 20 .. 30 s clips whose oracle-side worst top-1/top-2 gap is >= 4.8e-4 of max|logit|
+    # (scanned on the CPU with the same generator; see test_full_size_0p6b_batch8_30s_128_tokens)
+    sel = [(102, 27.8), (104, 23.0), (106, 20.1), (109, 24.7), (111, 22.8), (113, 24.5), (116, 30.0), (117, 27.9),
+           (118, 26.2), (119, 29.9), (120, 22.2), (122, 26.1), (123, 20.4), (124, 20.4), (125, 25.1), (127, 29.2)]
+    clips = [synth.make_clip(i, s) for i, s in sel]
     refs = [O.transcribe_ids(model, c, max_new_tokens=128, keep_logits=True, lm_head_all_rows=False) for c in clips]
     report["full_b16_min_rel_margin"] = min(_min_rel_margin(r) for r in refs)
     got = eng.transcribe_ids(clips, max_new_tokens=128)
     report["full_b16_stage_ms"] = got.stage_ms
-    assert report["full_b16_min_rel_margin"] >= MARGIN_FLOOR_REL
+    assert report["full_b16_min_rel_margin"] >= 5 * MARGIN_FLOOR_REL
     for b in range(16):
         assert got.ids[b] == refs[b].ids, b
 

@@ -17,9 +17,10 @@ for _ in range(2):
     r = eng.transcribe_ids(clips, max_new_tokens=32)
 print("batch", B, "stage_ms", r.stage_ms, "us/step", 1e3 * r.stage_ms["decode"] / max(r.decode_steps, 1))
 lib = _lib.load_library()
-buf = (C.c_longlong * 2048)()
-n = lib.asrb_debug_mega_timeline(buf, 2048)
-t = np.array(buf[:], dtype=np.int64).reshape(2, -1)
+buf = (C.c_longlong * 4096)()
+n = lib.asrb_debug_mega_timeline(buf, 4096)
+t = np.array(buf[:2048], dtype=np.int64).reshape(2, -1)
+gt = np.array(buf[2048:2048 + 8 * 148], dtype=np.int64).reshape(148, 8)
 L = cfg.text.num_hidden_layers
 names = ["x gather+norm", "qkv gemv", "attn items", "attn merge", "o_proj", "x gather+norm", "gate/up gemv", "down"]
 NP = len(names)
@@ -35,4 +36,11 @@ for cta, row in zip(("cta0", "ctaLast"), t):
     f = row[600:800]
     n = int((f != 0).sum())
     print(cta, "layer-5 fine marks (cycles since first):", [int(v - f[0]) for v in f[:n]])
+names_gt = ["x1 done", "qkv done", "items done", "merge done", "o_proj done", "gate/up done"]
+t0 = gt[:, 0].min()
+print("layer-5 wall clock per CTA (ns after the first CTA finished its x gather):", names_gt)
+for c in list(range(0, 148, 6)) + [140, 143, 146, 147]:
+    print(f"  cta {c:3d}:", " ".join(f"{int(v - t0):7d}" for v in gt[c, :6]))
+print("  max over CTAs:", " ".join(f"{int(v - t0):7d}" for v in gt[:, :6].max(0)), " argmax", gt[:, :6].argmax(0))
+print("  min over CTAs:", " ".join(f"{int(v - t0):7d}" for v in gt[:, :6].min(0)))
 eng.close()
