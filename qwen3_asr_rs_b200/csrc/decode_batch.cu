@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
     //  half a share of the items: range_start is piecewise linear in the CTA index)
     const int n_merge = min(nb * p.nkv, (int)G);
     const int c_merge = (int)G - n_merge;                             // first merging CTA
-    const long long W2 = 2LL * c_merge + n_merge;                     // total capacity in half shares
-    auto range_start = [&](int c) __attribute__((always_inline)) { const long long cw = c <= c_merge ? 2LL * c : 2LL * c_merge + (c - c_merge); return (int)((cw * T) / W2); };
+    const int W2 = 2 * c_merge + n_merge;                             // total capacity in half shares (cw * T < 2^21: 32-bit math)
+    auto range_start = [&](int c) __attribute__((always_inline)) { const int cw = c <= c_merge ? 2 * c : 2 * c_merge + (c - c_merge); return (int)(((unsigned)cw * (unsigned)T) / (unsigned)W2); };
     auto item_owner = [&](int t) __attribute__((always_inline)) {                                    // largest c with range_start(c) <= t
         int lo = 0, hi = (int)G - 1;
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (range_start(mid) <= t) lo = mid; else hi = mid - 1; }
@@ -308,6 +308,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
         xres[b * MAXROWS + r] = __ldcg(p.x + (size_t)b * H + xsl.r0 + r);
     }
     float best_v = -INFINITY; int best_i = 0x7fffffff;      // lm_head: running argmax of (tile row tid / NB, sequence tid % NB)
+    // merging CTA: which (sequence, kv head), and which record slots will be written for it -- slot u holds a record iff a
+    // run starts at split u, i.e. u == 0 or item base + u opens its owner's range.  Positions do not change within the
+    // step, so this is computed once, not per layer (the owner search is a dozen integer divisions per slot).
+    const int mid = (int)G - 1 - (int)blockIdx.x;
+    const bool merger = mid < nb * p.nkv;
+    const int mb_ = merger ? mid / p.nkv : 0, mg_ = merger ? mid - mb_ * p.nkv : 0;
+    unsigned merge_mask = 0;
+    if (merger) {
+        const int base_t = off_s[mb_] * p.nkv + mg_ * nact_s[mb_];
+        for (int u = 0; u < nact_s[mb_]; ++u)
+            if (u == 0 || range_start(item_owner(base_t + u)) == base_t + u) merge_mask |= 1u << u;
+    }
     // exchange regions of this step (set = epoch parity) and re-arm of the other set (words this CTA wrote last step)
     constexpr size_t SX_LAYER = (size_t)NB * (2 * H + QD + I);            // words per (set, layer): XO | XD | ATTN | ACT, each [seq][row]
     // (set = parity of the BATCHED-step counter bar[2]: the launch epoch bar[1] is shared with the single-sequence kernel,
@@ -585,9 +597,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
             // (long before the partial records), so RMSNorm + RoPE, the cache append and the new key's scores happen NOW,
             // off the tail of the phase
             float* mq = snew + 8;                     // [2][128] q heads of the merge (the item runs reuse qs)
-            const int mid = (int)G - 1 - (int)blockIdx.x;
-            const bool merger = mid < nb * p.nkv;
-            const int mb_ = merger ? mid / p.nkv : 0, mg_ = merger ? mid - mb_ * p.nkv : 0;
             if (merger) {
                 const float* cs = ropes + mb_ * 128; const float* sn = cs + 64;
                 const uint2* qkvb = p.qkv_ll + (size_t)mb_ * (QD + 2 * p.KVD);
@@ -720,12 +729,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_batch_kernel(const Params 
             // ---- merge of one (sequence, kv head): all its partial records + the current token's key / value ----
             if (merger) {
                 const int b = mb_, g = mg_;
-                const int base_t = off_s[b] * p.nkv + g * nact_s[b];
                 const int nact = nact_s[b];                                                        // record slots of (b, g)
-                // slot u holds a record iff a run starts at split u: u == 0 or item base_t + u opens its owner's range
-                auto run_start = [&](int u) { return u == 0 || range_start(item_owner(base_t + u)) == base_t + u; };
-                unsigned startmask = 0;
-                for (int u = 0; u < nact; ++u) startmask |= run_start(u) ? (1u << u) : 0u;
+                const unsigned startmask = merge_mask;
                 cons_sync();                          // kn / vn / snew of the early preparation are visible to every warp
                 {
                     const int hq = tid / HD, d = tid - hq * HD;          // hq is uniform per warp (HD = 4 warps)
