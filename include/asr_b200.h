@@ -111,6 +111,24 @@ ASRB_API int asrb_transcribe_ids(asrb_session* s, const float* const* samples, c
                         int batch, const int64_t* const* lang_ids, const int32_t* n_lang_ids,
                         int max_new_tokens, int32_t* ids_out, int32_t* lens_out);
 
+/* ---- GPU-side audio ingest (step 1 of transcribe(), load_audio_wav + resample, src/audio.rs:162-245) ----------- */
+/* Raw interleaved PCM of `batch` utterances (hound samples: s16 / s32 scaled by 2^-(bits-1), or f32; src/audio.rs:181-189)
+ * -> mono mixdown (mean over channels, :193-206) -> 16 kHz (:209-213) ON THE GPU, written straight into the session's
+ * sample buffer: the payload crosses PCIe once in its native format.  The resampler is the polyphase FIR of
+ * scipy.signal.resample_poly (the reference's rubato / swresample interpolators are not reproducible here); this stage
+ * is outside the parity point of the hot path and is pinned by its own golden (tests/test_gpu_parity.py).
+ * n_samples_out[b] = number of 16 kHz samples produced.  Follow with asrb_transcribe_ingested (or asrb_mel with
+ * samples == NULL). */
+#define ASRB_PCM_S16 0
+#define ASRB_PCM_F32 1
+#define ASRB_PCM_S32 2
+ASRB_API int asrb_ingest_pcm(asrb_session* s, const void* const* pcm, const int64_t* n_frames, const int32_t* channels,
+                    const int32_t* sample_rate, const int32_t* format, int batch, int64_t* n_samples_out);
+ASRB_API int asrb_ingested_read(asrb_session* s, int b, float* out /* [n_samples[b]] */);
+/* asrb_transcribe_ids on the utterances ingested by the last asrb_ingest_pcm */
+ASRB_API int asrb_transcribe_ingested(asrb_session* s, const int64_t* const* lang_ids, const int32_t* n_lang_ids,
+                             int max_new_tokens, int32_t* ids_out, int32_t* lens_out);
+
 /* Stage entry points = the calls transcribe() makes (each runs on the session stream;
  * *_read functions synchronise and copy to host, for parity tests). */
 /* WhisperFeatureExtractor::extract, src/mel.rs:49-96 (called at src/inference.rs:95) */

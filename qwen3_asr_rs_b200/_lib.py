@@ -15,7 +15,7 @@ SYMBOLS = [
     "asrb_model_dims", "asrb_model_free", "asrb_session_create", "asrb_session_free",
     "asrb_transcribe_ids", "asrb_mel", "asrb_mel_read", "asrb_encode", "asrb_encode_read",
     "asrb_prefill", "asrb_decode_step", "asrb_generate", "asrb_last_timings", "asrb_session_set_option",
-    "asrb_debug_mega_timeline", "asrb_session_stats", "asrb_session_device_ids", "asrb_model_lossy_tensors",
+    "asrb_debug_mega_timeline", "asrb_session_stats", "asrb_session_device_ids", "asrb_model_lossy_tensors", "asrb_ingest_pcm", "asrb_ingested_read", "asrb_transcribe_ingested",
 ]
 
 
@@ -76,6 +76,9 @@ def load_library() -> C.CDLL:
         "asrb_debug_mega_timeline": [P(C.c_longlong), C.c_int],
         "asrb_session_stats": [vp, P(i64), C.c_int],
         "asrb_session_device_ids": [vp, P(vp), P(vp), P(C.c_int), P(C.c_int)],
+        "asrb_ingest_pcm": [vp, P(vp), P(i64), P(i32), P(i32), P(i32), C.c_int, P(i64)],
+        "asrb_ingested_read": [vp, C.c_int, P(C.c_float)],
+        "asrb_transcribe_ingested": [vp, P(P(i64)), P(i32), C.c_int, P(i32), P(i32)],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

@@ -37,3 +37,25 @@ def load_wav(path: str, target_rate: int = 16000) -> np.ndarray:
         g = gcd(rate, target_rate)
         x = resample_poly(x.astype(np.float64), target_rate // g, rate // g).astype(np.float32)
     return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def read_wav_pcm(path: str):
+    """WAV payload as-is for the GPU ingest path (asrb_ingest_pcm): (interleaved array [frames, channels] of int16 / int32 /
+    float32, sample rate).  8-bit and 24-bit files are widened to int32 on the host (rare formats; hound does the same
+    widening, src/audio.rs:181-189)."""
+    with wave.open(path, "rb") as w:
+        nch, width, rate, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
+        raw = w.readframes(n)
+    if width == 2:
+        x = np.frombuffer(raw, dtype="<i2")
+    elif width == 4:
+        x = np.frombuffer(raw, dtype="<i4")
+    elif width == 3:
+        b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+        v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+        x = (np.where(v & 0x800000, v - (1 << 24), v) << 8).astype(np.int32)      # same value / 2^23 as int32 / 2^31
+    elif width == 1:
+        x = ((np.frombuffer(raw, dtype=np.uint8).astype(np.int32) - 128) << 24).astype(np.int32)
+    else:
+        raise ValueError(f"unsupported sample width {width}")
+    return np.ascontiguousarray(x.reshape(-1, nch)), rate

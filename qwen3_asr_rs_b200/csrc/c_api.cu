@@ -24,6 +24,9 @@ void session_transcribe_ids(Session* s, const float* const* samples, const int64
 void session_last_timings(Session* s, float* ms6, int64_t* kernels, int64_t* steps);
 void session_set_option(Session* s, const char* key, const char* value);
 void session_stats(Session* s, int64_t* out, int n);
+void session_ingest_pcm(Session* s, const void* const* pcm, const int64_t* n_frames, const int32_t* channels, const int32_t* rate,
+                        const int32_t* format, int batch, int64_t* n_samples_out);
+void session_ingested_read(Session* s, int b, float* out);
 void session_device_ids(Session* s, const int32_t** ids, const int32_t** lens, int* stride, int* batch);
 int decode_mega_debug_timeline(long long* out, int cap);
 int decode_batch_debug_timeline(long long* out, int cap);
@@ -164,6 +167,16 @@ int asrb_generate(asrb_session* s, int max_new_tokens, int32_t* ids_out, int32_t
 }
 int asrb_last_timings(asrb_session* s, float* ms_out6, int64_t* kernels_launched, int64_t* decode_steps) {
     return guarded([&] { NONNULL(s); session_last_timings(s->s, ms_out6, kernels_launched, decode_steps); });
+}
+int asrb_ingest_pcm(asrb_session* s, const void* const* pcm, const int64_t* n_frames, const int32_t* channels,
+                    const int32_t* sample_rate, const int32_t* format, int batch, int64_t* n_samples_out) {
+    return guarded([&] { NONNULL(s); NONNULL(pcm); NONNULL(n_frames); NONNULL(channels); NONNULL(sample_rate); NONNULL(format);
+                         session_ingest_pcm(s->s, pcm, n_frames, channels, sample_rate, format, batch, n_samples_out); });
+}
+int asrb_ingested_read(asrb_session* s, int b, float* out) { return guarded([&] { NONNULL(s); NONNULL(out); session_ingested_read(s->s, b, out); }); }
+int asrb_transcribe_ingested(asrb_session* s, const int64_t* const* lang_ids, const int32_t* n_lang_ids, int max_new_tokens,
+                             int32_t* ids_out, int32_t* lens_out) {
+    return guarded([&] { NONNULL(s); session_transcribe_ids(s->s, nullptr, nullptr, 0, lang_ids, n_lang_ids, max_new_tokens, ids_out, lens_out); });
 }
 int asrb_session_device_ids(asrb_session* s, const int32_t** ids_dev, const int32_t** lens_dev, int* row_stride, int* batch) {
     return guarded([&] { NONNULL(s); NONNULL(ids_dev); NONNULL(lens_dev); NONNULL(row_stride); NONNULL(batch);

@@ -11,6 +11,12 @@ namespace asrb {
 
 void model_set_tensor(Model* m, const char* name, int dtype, const int64_t* shape, int ndim, const void* host);
 void model_finalize(Model* m);
+struct IngestState;
+IngestState* ingest_state_new();
+void ingest_state_free(IngestState* st);
+void ingest_pcm(IngestState* st, cudaStream_t stream, const void* const* pcm, const int64_t* n_frames, const int32_t* channels,
+                const int32_t* rate, const int32_t* format, int batch, float* d_samples, int64_t max_samples_per_utt,
+                int64_t* n_out, int64_t* soff_out);
 
 // token ids of the fixed prompt (inference.rs:215-257) and special tokens (tokenizer.rs:53-59)
 static const int kPromptHead[9] = {151644, 8948, 198, 151645, 198, 151644, 872, 198, 151669};
@@ -63,6 +69,8 @@ struct Session {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float last_ms[6] = {0, 0, 0, 0, 0, 0};
     bool resident = false, timing = false;
+    IngestState* ingest = nullptr;      // GPU-side audio ingest (ingest.cu)
+    std::vector<int64_t> ingested_n;    // 16 kHz samples per utterance produced by the last asrb_ingest_pcm (empty: none pending)
     int64_t launches = 0, decode_steps = 0;
     int greedy_done = 0;   // greedy applications since prefill (tokens appended or EOS), bounds max_new
     ~Session();
@@ -79,6 +87,7 @@ Session::~Session() {
     if (h_ids) cudaFreeHost(h_ids);
     if (h_nout) cudaFreeHost(h_nout);
     if (h_next) cudaFreeHost(h_next);
+    if (ingest) ingest_state_free(ingest);
     if (st) cudaStreamDestroy(st);
 }
 
@@ -208,16 +217,18 @@ void session_free(Session* s) { delete s; }
 void session_mel(Session* s, const float* const* samples, const int64_t* n_samples, int batch, int64_t* n_frames_out) {
     ASRB_REQUIRE(batch >= 1 && batch <= s->max_batch, ASRB_ERR_INVALID, "batch exceeds session capacity");
     ASRB_CUDA_CHECK(cudaSetDevice(s->m->ctx->device));
+    const bool ingested = (samples == nullptr);          // samples already in HBM, written by asrb_ingest_pcm
+    if (ingested) ASRB_REQUIRE((int)s->ingested_n.size() == batch, ASRB_ERR_STATE, "no ingested audio for this batch");
     s->B = batch; s->stage = 0;
     s->n.assign(batch, 0); s->npad.assign(batch, 0); s->F.assign(batch, 0); s->foff.assign(batch, 0); s->soff.assign(batch, 0);
     int64_t so = 0, fo = 0; int maxF = 0;
     for (int b = 0; b < batch; ++b) {
-        int64_t n = n_samples[b];
-        ASRB_REQUIRE(samples[b] && n > 0 && n <= s->max_samples, ASRB_ERR_INVALID, "n_samples out of session capacity");
+        int64_t n = ingested ? s->ingested_n[b] : n_samples[b];
+        ASRB_REQUIRE((ingested || samples[b]) && n > 0 && n <= s->max_samples, ASRB_ERR_INVALID, "n_samples out of session capacity");
         int64_t np = ((n + 159) / 160) * 160;                                       // mel.rs:51
         ASRB_REQUIRE(np > 200, ASRB_ERR_INVALID, "utterance too short for reflect padding (needs > 200 samples)");
         s->n[b] = n; s->npad[b] = np; s->F[b] = np / 160; s->soff[b] = so; s->foff[b] = fo;
-        if (!s->resident) {
+        if (!s->resident && !ingested) {
             memcpy(s->h_samples + so, samples[b], n * sizeof(float));
             if (np > n) memset(s->h_samples + so + n, 0, (np - n) * sizeof(float));
         }
@@ -227,14 +238,35 @@ void session_mel(Session* s, const float* const* samples, const int64_t* n_sampl
     int64_t* h = s->h_i64; const int Bm = s->max_batch;
     for (int b = 0; b < batch; ++b) { h[b] = s->soff[b]; h[Bm + b] = s->n[b]; h[2 * Bm + b] = s->npad[b]; h[3 * Bm + b] = s->foff[b]; h[4 * Bm + b] = s->F[b]; }
     ASRB_CUDA_CHECK(cudaMemcpyAsync(s->d_i64, h, 5 * Bm * sizeof(int64_t), cudaMemcpyHostToDevice, s->st));
-    if (!s->resident)
+    if (!s->resident && !ingested)
         ASRB_CUDA_CHECK(cudaMemcpyAsync(s->d_samples, s->h_samples, so * sizeof(float), cudaMemcpyHostToDevice, s->st));
+    if (ingested) s->ingested_n.clear();                 // consumed
     if (s->timing) ASRB_CUDA_CHECK(cudaEventRecord(s->ev[1], s->st));
     launch_mel(*s->m, s->d_samples, s->d_i64, s->d_i64 + Bm, s->d_i64 + 2 * Bm, s->d_i64 + 3 * Bm, batch, maxF, s->d_mel,
                s->d_maxkey, s->st);
     s->launches += 3;
     if (n_frames_out) for (int b = 0; b < batch; ++b) n_frames_out[b] = s->F[b];
     s->stage = 1;
+}
+
+// step 1 on the GPU (src/audio.rs:162-245): raw interleaved PCM -> mono 16 kHz f32 in the session's sample buffer
+void session_ingest_pcm(Session* s, const void* const* pcm, const int64_t* n_frames, const int32_t* channels, const int32_t* rate,
+                        const int32_t* format, int batch, int64_t* n_samples_out) {
+    ASRB_REQUIRE(batch >= 1 && batch <= s->max_batch, ASRB_ERR_INVALID, "batch exceeds session capacity");
+    ASRB_CUDA_CHECK(cudaSetDevice(s->m->ctx->device));
+    if (!s->ingest) s->ingest = ingest_state_new();
+    std::vector<int64_t> n((size_t)batch), so((size_t)batch);
+    ingest_pcm(s->ingest, s->st, pcm, n_frames, channels, rate, format, batch, s->d_samples, s->max_samples, n.data(), so.data());
+    s->ingested_n = n;
+    s->stage = 0;
+    if (n_samples_out) for (int b = 0; b < batch; ++b) n_samples_out[b] = n[b];
+}
+void session_ingested_read(Session* s, int b, float* out) {
+    ASRB_REQUIRE(b >= 0 && b < (int)s->ingested_n.size(), ASRB_ERR_STATE, "ingested_read: nothing ingested for this index");
+    ASRB_CUDA_CHECK(cudaStreamSynchronize(s->st));
+    int64_t so = 0;
+    for (int i = 0; i < b; ++i) so += ((s->ingested_n[i] + 159) / 160) * 160;
+    ASRB_CUDA_CHECK(cudaMemcpy(out, s->d_samples + so, (size_t)s->ingested_n[b] * sizeof(float), cudaMemcpyDeviceToHost));
 }
 
 void session_mel_read(Session* s, int b, float* out) {
@@ -561,6 +593,7 @@ void session_transcribe_ids(Session* s, const float* const* samples, const int64
                             const int64_t* const* lang_ids, const int32_t* n_lang_ids, int max_new_tokens,
                             int32_t* ids_out, int32_t* lens_out) {
     ASRB_REQUIRE(ids_out && lens_out, ASRB_ERR_INVALID, "null output");
+    if (samples == nullptr) batch = (int)s->ingested_n.size();      // asrb_transcribe_ingested
     ASRB_REQUIRE(max_new_tokens >= 1 && max_new_tokens <= s->max_new, ASRB_ERR_INVALID, "max_new_tokens exceeds session capacity");
     cudaStream_t st = s->st;
     s->launches = 0; s->decode_steps = 0;

@@ -219,16 +219,68 @@ class AsrInference:
         names = ("h2d", "mel", "encoder", "prefill", "decode", "total")
         return TranscribeIds([ids[b, : n[b]].tolist() for b in range(B)], dict(zip(names, ms)), k.value, st.value)
 
+    # ---- GPU-side audio ingest (step 1, src/audio.rs:162-245) -------------------------------------------
+    _PCM_FMT = {"int16": 0, "float32": 1, "int32": 2}
+
+    def _ingest(self, pcms: Sequence, rates: Sequence[int], max_lang: int, max_new: int):
+        B = len(pcms)
+        arrs = [np.ascontiguousarray(a if a.ndim == 2 else a.reshape(-1, 1)) for a in pcms]
+        for a in arrs:
+            if a.dtype.name not in self._PCM_FMT:
+                raise ValueError(f"PCM dtype must be int16 / int32 / float32, got {a.dtype}")
+        n_out = [-(-a.shape[0] * MEL_SAMPLE_RATE // int(r)) for a, r in zip(arrs, rates)]
+        s = self._ensure_session(B, max(n_out), max_lang, max_new)
+        ptrs = (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
+        frames = (C.c_int64 * B)(*[a.shape[0] for a in arrs])
+        chans = (C.c_int32 * B)(*[a.shape[1] for a in arrs])
+        rts = (C.c_int32 * B)(*[int(r) for r in rates])
+        fmts = (C.c_int32 * B)(*[self._PCM_FMT[a.dtype.name] for a in arrs])
+        n = (C.c_int64 * B)()
+        _lib.check(self._lib.asrb_ingest_pcm(s, ptrs, frames, chans, rts, fmts, B, n))
+        return s, arrs, list(n)
+
+    def ingest_pcm(self, pcms: Sequence, rates: Sequence[int]) -> List[np.ndarray]:
+        """asrb_ingest_pcm + read-back (tests): interleaved PCM arrays [frames, channels] -> mono f32 @ 16 kHz, on the GPU."""
+        s, _keep, n = self._ingest(pcms, rates, 16, 64)
+        out = []
+        for b in range(len(pcms)):
+            a = np.empty(n[b], dtype=np.float32)
+            _lib.check(self._lib.asrb_ingested_read(s, b, a.ctypes.data_as(C.POINTER(C.c_float))))
+            out.append(a)
+        return out
+
+    def transcribe_pcm(self, pcms: Sequence, rates: Sequence[int], language_ids: Optional[Sequence] = None,
+                       max_new_tokens: int = MAX_NEW_TOKENS) -> TranscribeIds:
+        """transcribe() steps 1-8 for a batch with step 1 on the GPU: raw PCM in, token ids out."""
+        B = len(pcms)
+        keep, lptrs, llens, mx = self._pack_lang(language_ids, B)
+        s, _arrs, _n = self._ingest(pcms, rates, mx, max_new_tokens)
+        ids = np.zeros((B, max_new_tokens), dtype=np.int32)
+        n = np.zeros(B, dtype=np.int32)
+        _lib.check(self._lib.asrb_transcribe_ingested(s, lptrs, llens, int(max_new_tokens),
+                                                      ids.ctypes.data_as(C.POINTER(C.c_int32)), n.ctypes.data_as(C.POINTER(C.c_int32))))
+        ms = (C.c_float * 6)()
+        k, st = C.c_int64(), C.c_int64()
+        _lib.check(self._lib.asrb_last_timings(s, ms, C.byref(k), C.byref(st)))
+        names = ("h2d", "mel", "encoder", "prefill", "decode", "total")
+        return TranscribeIds([ids[b, : n[b]].tolist() for b in range(B)], dict(zip(names, ms)), k.value, st.value)
+
     def transcribe(self, audio_path: str, language: Optional[str] = None,
-                   max_new_tokens: int = MAX_NEW_TOKENS) -> TranscribeResult:
-        """AsrInference::transcribe (inference.rs:89-213): step 1 (WAV ingest, host) -> steps 2-8 on the GPU ->
-        step 9 (detokenise + parse, host; needs tokenizer.json, else raw_output is the id list as text)."""
-        from .audio import load_wav
+                   max_new_tokens: int = MAX_NEW_TOKENS, gpu_ingest: bool = True) -> TranscribeResult:
+        """AsrInference::transcribe (inference.rs:89-213): step 1 (WAV payload -> mono 16 kHz; on the GPU by default,
+        `gpu_ingest=False` = the host loader) -> steps 2-8 on the GPU -> step 9 (detokenise + parse, host; needs
+        tokenizer.json, else raw_output is the id list as text)."""
+        from .audio import load_wav, read_wav_pcm
         from .text import language_prompt_ids, parse_asr_output
-        samples = load_wav(audio_path, MEL_SAMPLE_RATE)
         lang_ids = language_prompt_ids(self.tokenizer, language)
-        r = self.transcribe_ids([samples], language_ids=[lang_ids] if lang_ids is not None else None,
-                                max_new_tokens=max_new_tokens)
+        if gpu_ingest:
+            pcm, rate = read_wav_pcm(audio_path)
+            r = self.transcribe_pcm([pcm], [rate], language_ids=[lang_ids] if lang_ids is not None else None,
+                                    max_new_tokens=max_new_tokens)
+        else:
+            samples = load_wav(audio_path, MEL_SAMPLE_RATE)
+            r = self.transcribe_ids([samples], language_ids=[lang_ids] if lang_ids is not None else None,
+                                    max_new_tokens=max_new_tokens)
         ids = r.ids[0]
         raw = self.tokenizer.decode(ids) if self.tokenizer is not None else " ".join(str(i) for i in ids)
         lang, text = parse_asr_output(raw, language is not None) if self.tokenizer is not None else ("unknown", raw)

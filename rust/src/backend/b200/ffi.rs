@@ -59,6 +59,9 @@ extern "C" {
     pub fn asrb_generate(s: *mut asrb_session, max_new_tokens: c_int, ids_out: *mut i32, lens_out: *mut i32) -> c_int;
 
     pub fn asrb_last_timings(s: *mut asrb_session, ms_out6: *mut f32, kernels_launched: *mut i64, decode_steps: *mut i64) -> c_int;
+    pub fn asrb_ingest_pcm(s: *mut asrb_session, pcm: *const *const c_void, n_frames: *const i64, channels: *const i32, sample_rate: *const i32, format: *const i32, batch: c_int, n_samples_out: *mut i64) -> c_int;
+    pub fn asrb_ingested_read(s: *mut asrb_session, b: c_int, out: *mut f32) -> c_int;
+    pub fn asrb_transcribe_ingested(s: *mut asrb_session, lang_ids: *const *const i64, n_lang_ids: *const i32, max_new_tokens: c_int, ids_out: *mut i32, lens_out: *mut i32) -> c_int;
     pub fn asrb_session_device_ids(s: *mut asrb_session, ids_dev: *mut *const i32, lens_dev: *mut *const i32, row_stride: *mut c_int, batch: *mut c_int) -> c_int;
     pub fn asrb_session_stats(s: *mut asrb_session, out: *mut i64, n: c_int) -> c_int;
     pub fn asrb_session_set_option(s: *mut asrb_session, key: *const c_char, value: *const c_char) -> c_int;

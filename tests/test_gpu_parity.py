@@ -502,3 +502,49 @@ def test_bad_config_json_is_a_status_not_a_crash(tiny, tmp_path):
     (d / "config.json").write_text(json.dumps(j))
     with pytest.raises(AsrbError):
         AsrInference.load(str(d), device=0)
+
+
+@pytest.mark.parametrize("rate,channels,dtype", [(24000, 2, "int16"), (44100, 1, "int16"), (48000, 2, "float32"),
+                                                 (8000, 1, "int16"), (16000, 3, "int32"), (22050, 2, "int16")])
+def test_gpu_ingest_matches_scipy_resample_poly(tiny_engine, rate, channels, dtype):
+    """asrb_ingest_pcm (src/audio.rs:162-245 on the GPU): sample scaling, mono mixdown and the polyphase resampler against
+    its own golden, scipy.signal.resample_poly on the f64 mono signal (the host loader of audio.py)."""
+    from math import gcd
+    from scipy.signal import resample_poly
+    rng = np.random.default_rng(rate + channels)
+    n = int(rate * 1.37) + 11
+    t = np.arange(n) / rate
+    sig = np.stack([0.4 * np.sin(2 * np.pi * (220.0 + 90 * c) * t) + 0.05 * rng.standard_normal(n) for c in range(channels)], 1)
+    if dtype == "int16":
+        pcm = np.clip(np.round(sig * 32767), -32768, 32767).astype(np.int16); f = pcm.astype(np.float32) / 32768.0
+    elif dtype == "int32":
+        pcm = np.round(sig * 2147483000.0).astype(np.int32); f = pcm.astype(np.float32) / 2147483648.0
+    else:
+        pcm = sig.astype(np.float32); f = pcm
+    mono = f.sum(axis=1, dtype=np.float32) / np.float32(channels) if channels > 1 else f[:, 0]
+    g = gcd(rate, 16000)
+    ref = mono.astype(np.float32) if rate == 16000 else resample_poly(mono.astype(np.float64), 16000 // g, rate // g).astype(np.float32)
+    got = tiny_engine.ingest_pcm([pcm], [rate])[0]
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 2e-6
+
+
+def test_transcribe_pcm_equals_host_ingest(tiny, tiny_engine):
+    """steps 1-8 with step 1 on the GPU == host loader + steps 2-8 (same ids), batch of two different formats."""
+    from math import gcd
+    from scipy.signal import resample_poly
+    _, _, model = tiny
+    x24 = synth.make_clip(77, 2.0, sample_rate=24000)
+    x48 = synth.make_clip(78, 1.3, sample_rate=48000)
+    pcm24 = (np.stack([x24, x24], 1) * 32767).astype(np.int16)
+    pcm48 = x48.astype(np.float32).reshape(-1, 1)
+    host = []
+    for pcm, rate in ((pcm24, 24000), (pcm48, 48000)):
+        f = pcm.astype(np.float32) / (32768.0 if pcm.dtype == np.int16 else 1.0)
+        mono = f.mean(axis=1)
+        g = gcd(rate, 16000)
+        host.append(resample_poly(mono.astype(np.float64), 16000 // g, rate // g).astype(np.float32))
+    want = tiny_engine.transcribe_ids(host, max_new_tokens=10).ids
+    got = tiny_engine.transcribe_pcm([pcm24, pcm48], [24000, 48000], max_new_tokens=10).ids
+    assert got == want
+    assert got[0] == O.transcribe_ids(model, host[0], max_new_tokens=10).ids
