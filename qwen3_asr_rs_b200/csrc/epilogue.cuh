@@ -48,16 +48,17 @@ __device__ __forceinline__ void epi_store2(const GemmEpi& e, int N, int m, int n
             }
             break;
         }
-        case EPI_CONV_FEAT: {     // conv3 -> [chunk*OW + ow][c*OH + oh]  (permute(0,3,1,2).reshape)
+        case EPI_CONV_FEAT: {     // conv3 -> [chunk*OW + ow][oh*N + c]: permute(0,3,1,2).reshape with the feature index
+                                  // transposed (c*OH + oh -> oh*N + c; conv_out.weight is permuted to match, model.cu)
             int per = e.OH * e.OW;
             int chunk = m / per, r = m - chunk * per;
             int oh = r / e.OW, ow = r - oh * e.OW;
             size_t row = (size_t)chunk * e.OW + ow;
             v0 = gelu_erf(v0 + e.bias[n]);
-            store_split3(e.out_s3, e.s3_plane_stride, row * e.lds + (size_t)n * e.OH + oh, v0);
+            store_split3(e.out_s3, e.s3_plane_stride, row * e.lds + (size_t)oh * N + n, v0);
             if (has1) {
                 v1 = gelu_erf(v1 + e.bias[n + 1]);
-                store_split3(e.out_s3, e.s3_plane_stride, row * e.lds + (size_t)(n + 1) * e.OH + oh, v1);
+                store_split3(e.out_s3, e.s3_plane_stride, row * e.lds + (size_t)oh * N + n + 1, v1);
             }
             break;
         }
@@ -114,6 +115,85 @@ __device__ __forceinline__ void store_split3_x8(bf16* base, size_t plane_stride,
     *reinterpret_cast<uint4*>(base + idx) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(base + plane_stride + idx) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
     *reinterpret_cast<uint4*>(base + 2 * plane_stride + idx) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// 4 consecutive bf16 per plane = one 8-byte store per plane
+__device__ __forceinline__ void store_split3_x4(bf16* base, size_t plane_stride, size_t idx, const float* v) {
+    const Split3 a = split3(v[0]), b = split3(v[1]), c = split3(v[2]), d = split3(v[3]);
+    auto pk = [](bf16 x, bf16 y) { return (uint32_t)__bfloat16_as_ushort(x) | ((uint32_t)__bfloat16_as_ushort(y) << 16); };
+    *reinterpret_cast<uint2*>(base + idx) = make_uint2(pk(a.hi, b.hi), pk(c.hi, d.hi));
+    *reinterpret_cast<uint2*>(base + plane_stride + idx) = make_uint2(pk(a.mid, b.mid), pk(c.mid, d.mid));
+    *reinterpret_cast<uint2*>(base + 2 * plane_stride + idx) = make_uint2(pk(a.lo, b.lo), pk(c.lo, d.lo));
+}
+
+// Epilogue unit of the tcgen05 GEMM after its shared-memory transpose: one lane owns 4 consecutive columns n..n+3
+// (n % 4 == 0) of row m, 8 lanes cover 32 consecutive columns of a row, so a warp store instruction writes whole 128-byte
+// lines (fp32 rows) / whole 32-byte sectors (bf16 planes).  Same arithmetic as epi_store2 / epi_store8.
+// The global READS of the epilogue (bias, residual, positional row, row map) are split from the stores: the compiler must
+// keep a load behind any earlier store that may alias, so a load-inside-the-store-loop epilogue pays one L2 round trip
+// per iteration (measured: 18 k cycles per 128x128 tile with a bias, 50 k with a residual).  The caller issues the
+// epi_fetch4 calls of a group of rows first, then the epi_store4 calls.
+struct EpiIn { float4 add; int tok; };
+template <int MODE>
+__device__ __forceinline__ float4 epi_bias4(const GemmEpi& e, int n) {
+    const bool has = (MODE == EPI_CONV_PARITY || MODE == EPI_CONV_FEAT) ? true : (MODE == EPI_SWIGLU ? false : e.bias != nullptr);
+    return has ? __ldg(reinterpret_cast<const float4*>(e.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+template <int MODE>
+__device__ __forceinline__ EpiIn epi_fetch4(const GemmEpi& e, int N, int m, int n) {
+    EpiIn in; in.add = make_float4(0.f, 0.f, 0.f, 0.f); in.tok = 0;
+    if (MODE == EPI_PLAIN) {
+        // plain load: the residual may be the output buffer (x += proj(...)); this thread reads exactly the elements it
+        // later overwrites
+        if (e.residual) in.add = *reinterpret_cast<const float4*>(e.residual + (size_t)m * e.ldr + n);
+    } else if (MODE == EPI_CONVOUT) {
+        in.tok = __ldg(e.row_map + m);
+        in.add = __ldg(reinterpret_cast<const float4*>(e.pos + (size_t)(m % e.pos_period) * N + n));
+    }
+    return in;
+}
+template <int MODE>
+__device__ __forceinline__ void epi_store4(const GemmEpi& e, int N, int m, int n, float4 a, float4 b, const EpiIn& in) {
+    float v[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};          // + bias (zero when there is none)
+    if (MODE == EPI_PLAIN) {
+        if (e.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = gelu_erf(v[i]);
+        }
+        if (e.residual) { v[0] += in.add.x; v[1] += in.add.y; v[2] += in.add.z; v[3] += in.add.w; }
+        if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + (size_t)m * e.ldo + n) = make_float4(v[0], v[1], v[2], v[3]);
+        if (e.out_s3) store_split3_x4(e.out_s3, e.s3_plane_stride, (size_t)m * e.lds + n, v);
+    } else if (MODE == EPI_CONV_PARITY || MODE == EPI_CONV_FEAT) {
+        const int per = e.OH * e.OW;
+        const int chunk = m / per, r = m - chunk * per;
+        const int oh = r / e.OW, ow = r - oh * e.OW;
+        size_t idx;
+        if (MODE == EPI_CONV_PARITY) {
+            idx = ((((size_t)chunk * 2 + (oh & 1)) * 2 + (ow & 1)) * e.Hh2 + (oh >> 1)) * e.Wh2 + (ow >> 1);
+            idx = idx * e.cpad + n;
+        } else {
+            idx = ((size_t)chunk * e.OW + ow) * e.lds + (size_t)oh * N + n;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = gelu_erf(v[i]);
+        store_split3_x4(e.out_s3, e.s3_plane_stride, idx, v);
+    } else if (MODE == EPI_CONVOUT) {
+        if (in.tok < 0) return;
+        *reinterpret_cast<float4*>(e.out_f32 + (size_t)in.tok * e.ldo + n) =
+            make_float4(v[0] + in.add.x, v[1] + in.add.y, v[2] + in.add.z, v[3] + in.add.w);
+    } else {   // EPI_SWIGLU: columns (gate_j, up_j) x 2 -> 2 outputs
+        const float o0 = silu(v[0]) * v[1], o1 = silu(v[2]) * v[3];
+        const size_t j = (size_t)(n >> 1);
+        if (e.out_f32) *reinterpret_cast<float2*>(e.out_f32 + (size_t)m * e.ldo + j) = make_float2(o0, o1);
+        if (e.out_s3) {
+            const Split3 a0 = split3(o0), a1 = split3(o1);
+            auto pk = [](bf16 x, bf16 y) { return (uint32_t)__bfloat16_as_ushort(x) | ((uint32_t)__bfloat16_as_ushort(y) << 16); };
+            const size_t idx = (size_t)m * e.lds + j;
+            *reinterpret_cast<uint32_t*>(e.out_s3 + idx) = pk(a0.hi, a1.hi);
+            *reinterpret_cast<uint32_t*>(e.out_s3 + e.s3_plane_stride + idx) = pk(a0.mid, a1.mid);
+            *reinterpret_cast<uint32_t*>(e.out_s3 + 2 * e.s3_plane_stride + idx) = pk(a0.lo, a1.lo);
+        }
+    }
 }
 
 template <int MODE>
@@ -184,9 +264,16 @@ __device__ __forceinline__ void epi_store8(const GemmEpi& e, int N, int m, int n
             *reinterpret_cast<uint2*>(e.out_s3 + e.s3_plane_stride + idx) = make_uint2(mid[0], mid[1]);
             *reinterpret_cast<uint2*>(e.out_s3 + 2 * e.s3_plane_stride + idx) = make_uint2(lo[0], lo[1]);
         }
-    } else {   // EPI_CONV_FEAT (strided): pairwise path
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) epi_store2(e, N, m, n + i, acc[i], acc[i + 1], true);
+    } else {   // EPI_CONV_FEAT: 8 consecutive channels of (chunk, ow, oh) are contiguous in the transposed feature layout
+        const int per = e.OH * e.OW;
+        const int chunk = m / per, r = m - chunk * per;
+        const int oh = r / e.OW, ow = r - oh * e.OW;
+        const size_t row = (size_t)chunk * e.OW + ow;
+        float v[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(e.bias + n), b1 = *reinterpret_cast<const float4*>(e.bias + n + 4);
+        v[0] = gelu_erf(acc[0] + b0.x); v[1] = gelu_erf(acc[1] + b0.y); v[2] = gelu_erf(acc[2] + b0.z); v[3] = gelu_erf(acc[3] + b0.w);
+        v[4] = gelu_erf(acc[4] + b1.x); v[5] = gelu_erf(acc[5] + b1.y); v[6] = gelu_erf(acc[6] + b1.z); v[7] = gelu_erf(acc[7] + b1.w);
+        store_split3_x8(e.out_s3, e.s3_plane_stride, row * e.lds + (size_t)oh * N + n, v);
     }
 }
 

@@ -6,7 +6,7 @@
 // 128-129) as implicit GEMM.  B200-native structure: one 128x128 output tile per CTA, operands
 // staged by TMA (cp.async.bulk.tensor, 128B swizzle) into a 3-stage shared-memory ring, a single
 // elected thread issues tcgen05.mma (kind::f16, M=128 N=128 K=16) accumulating in TMEM (fp32),
-// tcgen05.commit releases ring slots / signals the epilogue, four epilogue warps read the
+// tcgen05.commit releases ring slots / signals the epilogue, eight epilogue warps read the
 // accumulator with tcgen05.ld and apply the fused epilogues of epilogue.cuh.
 //
 // Precision: weights are exact bf16; each fp32 activation is stored as 3 bf16 planes
@@ -32,8 +32,11 @@ static constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
 static constexpr int TILE_A_BYTES = BM * BK * 2;      // 16 KB per plane
 static constexpr int TILE_B_BYTES = BN * BK * 2;      // 16 KB
 static constexpr int STAGE_BYTES = 3 * TILE_A_BYTES + TILE_B_BYTES;   // 64 KB
-static constexpr int NTHREADS = 192;                  // warp0 TMA, warp1 MMA, warps 2-5 epilogue
-static constexpr int TMEM_COLS = 256;                 // two 128-column fp32 accumulators (ping-pong)
+static constexpr int NTHREADS = 320;                  // warp0 TMA, warp1 MMA, warps 2-9 epilogue
+static constexpr int EPI_WARPS = 8, EC = 64;          // epilogue warps, accumulator columns per epilogue warp
+static constexpr int NACC = 4;                         // 128-column fp32 TMEM accumulators in rotation
+static constexpr int TMEM_COLS = NACC * 128;           // all 512 columns: the MMA warp may run a whole short-K tile ahead of the epilogue
+static constexpr int SLAB_LD = 20;                     // floats per staged epilogue row (16 + 4: 16-byte aligned, conflict-free)
 static constexpr int CH = 4;                          // k-blocks (of 64) accumulated inside the tensor core per chunk
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -119,17 +122,23 @@ struct ConvGeom { int OH, OW, box_h, tiles_per_chunk, kblk_per_tap, a_box_bytes;
 // So the tensor core only accumulates CH k-blocks (K = 256) at a time into one of two TMEM
 // accumulators; the epilogue warps drain each finished chunk with tcgen05.ld and add it into fp32
 // registers (round-to-nearest) while the MMA warp fills the other accumulator.
+// ASRB_GEMM_DEBUG timeline: CTAs 0 and 80 record clock64 stamps [cta][role: 0 TMA, 1 MMA, 2 epilogue][item < 8][4]
+#define DBG_ON (E.dbg != nullptr && (blockIdx.x == 0 || blockIdx.x == 80))
+#define DBG_VAL(role, it, k, v) do { if (DBG_ON && (it) < 8) E.dbg[(((blockIdx.x ? 1 : 0) * 3 + (role)) * 8 + (it)) * 4 + (k)] = (v); } while (0)
+#define DBG_STAMP(role, it, k) DBG_VAL(role, it, k, clock64())
+
 template <int A_MODE, int EPI_MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               int M, int N, int K, int nplanes, int tiles_m, int tiles_n, int splits, ConvGeom cg, GemmEpi E) {
+               int M, int N, int K, int nplanes, int tiles_m, int tiles_n, int splits, int nacc, ConvGeom cg, GemmEpi E) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
-    uint64_t* acc_full = empty + STAGES;      // [2]
-    uint64_t* acc_empty = acc_full + 2;       // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* acc_full = empty + STAGES;      // [NACC]
+    uint64_t* acc_empty = acc_full + NACC;    // [NACC]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
+    float* epi_slab = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // EPI_WARPS x [32][SLAB_LD]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Persistent CTAs: work item = (m tile, n tile, k split), dealt round-robin (item = blockIdx.x + i * gridDim.x; n
     // fastest so that concurrently running CTAs share the A tile in L2).  The three roles keep GLOBAL stage / chunk
@@ -143,7 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
@@ -172,10 +181,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t a_bytes = (A_MODE == 0) ? (uint32_t)TILE_A_BYTES : (uint32_t)cg.a_box_bytes;
         const uint32_t stage_tx = (uint32_t)nplanes * a_bytes + (uint32_t)TILE_B_BYTES;
         uint32_t kg = 0;                                   // global k-block counter (ring position)
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             int n0, m0, chunk, oh0, z;
             item_coords(item, n0, m0, chunk, oh0, z);
             const int kb0 = z * num_kb;
+            DBG_STAMP(0, it, 0);
             for (int kb = 0; kb < num_kb; ++kb, ++kg) {
                 const int s = kg % STAGES; const uint32_t par = (kg / STAGES) & 1;
                 mbar_wait(&empty[s], par ^ 1);
@@ -193,18 +204,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
                 tma_load_2d(st + 3 * TILE_A_BYTES, &mapB, (kb0 + kb) * BK, n0, &full[s]);
             }
+            DBG_STAMP(0, it, 1);
         }
     } else if (warp == 1 && lane == 0) {
         // ================= MMA issuer =================
         const uint32_t idesc = make_idesc();
         uint32_t kg = 0, cgl = 0;                          // global k-block / chunk counters
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            long long w_acc = 0, w_full = 0;
+            DBG_STAMP(1, it, 0);
             for (int kb = 0; kb < num_kb; ++kb, ++kg) {
                 const int s = kg % STAGES; const uint32_t par = (kg / STAGES) & 1;
-                const int cb = cgl & 1;                                     // accumulator buffer of the current chunk
+                const int cb = cgl % nacc;                                  // accumulator buffer of the current chunk
                 const bool chunk_first = (kb % CH) == 0;
-                if (chunk_first) { mbar_wait(&acc_empty[cb], ((cgl >> 1) & 1) ^ 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+                long long tw0 = DBG_ON ? clock64() : 0;
+                if (chunk_first) { mbar_wait(&acc_empty[cb], ((cgl / nacc) & 1) ^ 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+                long long tw1 = DBG_ON ? clock64() : 0;
                 mbar_wait(&full[s], par);
+                if (DBG_ON) { w_acc += tw1 - tw0; w_full += clock64() - tw1; }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                 const uint64_t bdesc = make_smem_desc(sa + 3 * TILE_A_BYTES);
@@ -218,27 +236,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 umma_commit(&empty[s]);                   // slot reusable once these MMAs retire
                 if ((kb % CH) == CH - 1 || kb == num_kb - 1) { umma_commit(&acc_full[cb]); ++cgl; }
             }
+            DBG_STAMP(1, it, 1); DBG_VAL(1, it, 2, w_acc); DBG_VAL(1, it, 3, w_full);
         }
     } else if (warp >= 2) {
         // ================= epilogue =================
-        const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
-        const int r = quad * 32 + lane;               // row inside the tile
+        // 8 warps: warp w reads TMEM lane quadrant w & 3 (its 32 accumulator rows) and owns EC = 64 of the tile's 128
+        // columns.  (With 4 warps x 128 columns the GELU / split3 epilogues ran 29 k cycles per tile on one warp per
+        // scheduler, longer than a K = 896 main loop; two warps per scheduler halve that and overlap each other's latency.)
+        const int quad = warp & 3;
+        const int hb = ((warp - 2) >> 2) * EC;        // first tile column of this warp
         const int num_chunks = (num_kb + CH - 1) / CH;
         uint32_t cgl = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             int n0, m0, chunk, oh0, z;
             item_coords(item, n0, m0, chunk, oh0, z);
-            float accum[BN];
+            long long w_wait = 0;
+            float accum[EC];
 #pragma unroll
-            for (int j = 0; j < BN; ++j) accum[j] = 0.f;
+            for (int j = 0; j < EC; ++j) accum[j] = 0.f;
             for (int c = 0; c < num_chunks; ++c, ++cgl) {
-                const int cb = cgl & 1;
-                mbar_wait(&acc_full[cb], (cgl >> 1) & 1);
+                const int cb = cgl % nacc;
+                long long tw0 = DBG_ON ? clock64() : 0;
+                mbar_wait(&acc_full[cb], (cgl / nacc) & 1);
+                if (DBG_ON) { w_wait += clock64() - tw0; if (c == 0 && threadIdx.x == 64) DBG_STAMP(2, it, 0); }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = 0; c0 < EC; c0 += 32) {
                     uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * BN + c0), v);
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * BN + hb + c0), v);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) accum[c0 + j] += __uint_as_float(v[j]);
                 }
@@ -246,19 +272,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[cb])) : "memory");
             }
-            long long m = -1;
-            if (A_MODE == 0) { if (m0 + r < M) m = m0 + r + (long long)z * M; }
-            else {
-                const int oh = oh0 + r / cg.OW, ow = r % cg.OW;
-                if (r < cg.box_h * cg.OW && oh < cg.OH) m = ((long long)chunk * cg.OH + oh) * cg.OW + ow;
-            }
-            if (m >= 0) {
+            if (threadIdx.x == 64) { DBG_STAMP(2, it, 1); DBG_VAL(2, it, 3, w_wait); }
+            // Store through a per-warp shared-memory transpose.  A thread owns one accumulator ROW (its TMEM lane), so
+            // storing from the registers directly makes every store instruction touch 32 different rows.  Instead each
+            // warp stages 16 columns of its 32 rows ([32][20] floats, conflict-free for 128-bit accesses), then lane l
+            // re-reads columns 4*(l&3).. of rows 8*i + (l>>2): a warp store instruction covers 8 rows x 64 contiguous bytes.
+            float* slab = epi_slab + (warp - 2) * (32 * SLAB_LD);
+            const int lr = lane >> 2, lc = (lane & 3) * 4;
 #pragma unroll
-                for (int j = 0; j < BN; j += 8) {
-                    const int n = n0 + j;
-                    if (n < N) epi_store8<EPI_MODE>(E, N, (int)m, n, &accum[j]);
+            for (int c0 = 0; c0 < EC; c0 += 16) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(slab + lane * SLAB_LD + j) = make_float4(accum[c0 + j], accum[c0 + j + 1], accum[c0 + j + 2], accum[c0 + j + 3]);
+                __syncwarp();
+                const int n = n0 + hb + c0 + lc;
+                const bool ncol = n < N;
+                const float4 bias4 = ncol ? epi_bias4<EPI_MODE>(E, n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 v[4]; long long mr[4]; EpiIn in[4];            // 4 rows per lane: every global load first, then the stores
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = quad * 32 + 8 * i + lr;            // row inside the tile
+                    v[i] = *reinterpret_cast<const float4*>(slab + (8 * i + lr) * SLAB_LD + lc);
+                    long long m = -1;
+                    if (A_MODE == 0) { if (m0 + rr < M) m = m0 + rr + (long long)z * M; }
+                    else {
+                        const int oh = oh0 + rr / cg.OW, ow = rr % cg.OW;
+                        if (rr < cg.box_h * cg.OW && oh < cg.OH) m = ((long long)chunk * cg.OH + oh) * cg.OW + ow;
+                    }
+                    mr[i] = (m >= 0 && ncol) ? m : -1;
+                    if (mr[i] >= 0) in[i] = epi_fetch4<EPI_MODE>(E, N, (int)mr[i], n);
                 }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (mr[i] >= 0) epi_store4<EPI_MODE>(E, N, (int)mr[i], n, v[i], bias4, in[i]);
+                __syncwarp();
             }
+            if (threadIdx.x == 64) DBG_STAMP(2, it, 2);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -337,12 +386,56 @@ static int sm_count() {
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n;
 }
-static size_t smem_bytes() { return (size_t)STAGES * STAGE_BYTES + 1024 + 256; }   // stages + alignment slack + barriers
+static size_t smem_bytes() { return (size_t)STAGES * STAGE_BYTES + 1024 + 256 + EPI_WARPS * 32 * SLAB_LD * 4; }   // stages + alignment slack + barriers + epilogue slabs
 
 }  // namespace tc
 
-bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& E, cudaStream_t st) {
+// ASRB_GEMM_DEBUG="M,N,K": the next matching launch records the per-role timeline and prints it (debug builds of a trip)
+static void gemm_debug_dump(long long* d_dbg, int M, int N, int K, cudaStream_t st) {
+    long long h[2 * 3 * 8 * 4];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[gemm_tc timeline] M=%d N=%d K=%d (cycles relative to the CTA's first stamp)\n", M, N, K);
+    for (int c = 0; c < 2; ++c) {
+        const long long t0 = h[((c * 3 + 0) * 8 + 0) * 4 + 0];
+        for (int it = 0; it < 8; ++it) {
+            const long long* p = &h[((c * 3 + 0) * 8 + it) * 4]; const long long* q = &h[((c * 3 + 1) * 8 + it) * 4];
+            const long long* e = &h[((c * 3 + 2) * 8 + it) * 4];
+            if (!p[0]) break;
+            fprintf(stderr, "  cta%d item%d  tma %lld..%lld | mma %lld..%lld wait_acc %lld wait_full %lld | epi first %lld drained %lld stored %lld wait %lld\n",
+                    c ? 80 : 0, it, p[0] - t0, p[1] - t0, q[0] - t0, q[1] - t0, q[2], q[3], e[0] - t0, e[1] - t0, e[2] - t0, e[3]);
+        }
+    }
+}
+
+bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& Ein, cudaStream_t st) {
     using namespace tc;
+    GemmEpi E = Ein;
+    static long long* d_dbg = nullptr; static int dbgM = -1, dbgN = 0, dbgK = 0, dbg_left = 0;
+    if (dbgM == -1) {
+        dbgM = 0;
+        if (const char* e = getenv("ASRB_GEMM_DEBUG")) {
+            if (sscanf(e, "%d,%d,%d", &dbgM, &dbgN, &dbgK) == 3) { cudaMalloc(&d_dbg, 2 * 3 * 8 * 4 * 8); dbg_left = 2; } else dbgM = 0;
+        }
+    }
+    const bool dbg_this = dbg_left > 0 && A.M == dbgM && N == dbgN && A.K == dbgK;
+    if (dbg_this) { cudaMemsetAsync(d_dbg, 0, 2 * 3 * 8 * 4 * 8, st); E.dbg = d_dbg; --dbg_left; }
+    struct Dump { bool on; long long* d; int M, N, K; cudaStream_t st; ~Dump() { if (on) gemm_debug_dump(d, M, N, K, st); } } dump{dbg_this, d_dbg, A.M, N, A.K, st};
+    // ASRB_GEMM_TIME=1: CUDA-event time of every launch (synchronises per launch; measurement runs only)
+    static const bool time_all = getenv("ASRB_GEMM_TIME") != nullptr;
+    struct Timer {
+        bool on; cudaEvent_t e0, e1; int M, N, K, mode; cudaStream_t st;
+        Timer(bool o, int M_, int N_, int K_, int mode_, cudaStream_t s) : on(o), M(M_), N(N_), K(K_), mode(mode_), st(s) {
+            if (on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+        }
+        ~Timer() {
+            if (!on) return;
+            cudaEventRecord(e1, st); cudaEventSynchronize(e1);
+            float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+            fprintf(stderr, "[gemm_tc time] M=%d N=%d K=%d epi=%d %.1f us\n", M, N, K, mode, ms * 1000.f);
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+        }
+    } timer(time_all || dbg_this, A.M, N, A.K, E.mode, st);
     if (A.K % BK != 0 || A.M <= 0 || N <= 0) return false;
     if (A.nplanes < 1 || A.nplanes > 3) return false;
     if ((reinterpret_cast<uintptr_t>(A.a) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) return false;
@@ -353,6 +446,7 @@ bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& E, cuda
     const CUtensorMap mapB = cached_map(W, 2, bd, bs, bb);
     ConvGeom cg{};
     const size_t smem = smem_bytes();
+    static const int nacc = [] { const char* e = getenv("ASRB_GEMM_NACC"); int v = e ? atoi(e) : NACC; return (v == 2 || v == 4) ? v : NACC; }();
     if (N % 8 != 0) return false;
     if (A.mode == A_PLAIN) {
         if (A.plane_stride % 8 != 0 && A.nplanes > 1) return false;
@@ -377,7 +471,7 @@ bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& E, cuda
             P.out_f32 = E.splitk_ws; P.ldo = N;
             // (the attribute is per device: set on every launch, a process may hold contexts on several GPUs)
             ASRB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<0, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gemm_tc_kernel<0, EPI_PLAIN><<<std::min(tiles * splits, sms), NTHREADS, smem, st>>>(mapA, mapB, A.M, N, A.K, A.nplanes, tiles_m, tiles_n, splits, cg, P);
+            gemm_tc_kernel<0, EPI_PLAIN><<<std::min(tiles * splits, sms), NTHREADS, smem, st>>>(mapA, mapB, A.M, N, A.K, A.nplanes, tiles_m, tiles_n, splits, nacc, cg, P);
             const int work = A.M * (N / 8);
             splitk_reduce_kernel<<<(work + 255) / 256, 256, 0, st>>>(E.splitk_ws, splits, A.M, N, E);
             ASRB_CUDA_CHECK(cudaGetLastError());
@@ -387,7 +481,7 @@ bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& E, cuda
 #define ASRB_TC_LAUNCH(AM, EM)                                                                                         \
     {                                                                                                                  \
         ASRB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<AM, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        gemm_tc_kernel<AM, EM><<<std::min(tiles_m * tiles_n, sms), NTHREADS, smem, st>>>(mapA, mapB, A.M, N, A.K, A.nplanes, tiles_m, tiles_n, 1, cg, E); \
+        gemm_tc_kernel<AM, EM><<<std::min(tiles_m * tiles_n, sms), NTHREADS, smem, st>>>(mapA, mapB, A.M, N, A.K, A.nplanes, tiles_m, tiles_n, 1, nacc, cg, E); \
     }
         if (E.mode == EPI_PLAIN) ASRB_TC_LAUNCH(0, EPI_PLAIN)
         else if (E.mode == EPI_SWIGLU) ASRB_TC_LAUNCH(0, EPI_SWIGLU)

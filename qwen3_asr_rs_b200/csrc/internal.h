@@ -123,6 +123,7 @@ struct GemmEpi {
     // optional fp32 workspace for split-K (EPI_PLAIN GEMMs with too few tiles to fill the GPU): >= SPLITK_WS_FLOATS floats
     float* splitk_ws = nullptr;
     int64_t* extra_launches = nullptr;   // incremented by the number of kernels launched beyond the one GEMM kernel
+    long long* dbg = nullptr;            // ASRB_GEMM_DEBUG timeline (gemm_tc.cu), null in production
 };
 static constexpr size_t SPLITK_WS_FLOATS = (size_t)4 * 64 * 128 * 128;   // 4 splits x 64 tiles of 128 x 128
 enum { GEMM_SIMT = 0, GEMM_TC = 1 };

@@ -191,6 +191,17 @@ __global__ void repack_conv_kernel(const bf16* __restrict__ src, bf16* __restric
     }
 }
 
+// conv_out.weight [dm][c*OH + oh] -> [dm][oh*dsh + c]: the conv3 epilogue then writes 8 consecutive channels of one
+// (chunk, ow, oh) as one 16-byte store per plane instead of 2-byte stores 2*OH bytes apart (the contraction over the
+// 7680 features is the same sum in a different order)
+__global__ void permute_convout_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, size_t rows, int dsh, int OH) {
+    const size_t feat = (size_t)dsh * OH, total = rows * feat;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / feat; const int k = (int)(i - r * feat); const int oh = k / dsh, c = k - oh * dsh;
+        dst[i] = src[r * feat + (size_t)c * OH + oh];
+    }
+}
+
 static void build_mel_tables(Model* m) {
     // mel.rs:115-187, f64 -> f32 with the reference's f32 multiply by enorm
     const int num_mels = m->d.c.num_mel_bins, n_fft = 400, n_freqs = 201;
@@ -299,7 +310,15 @@ void model_finalize(Model* m) {
         if (!b) { std::vector<float> z(dsh, 0.f); b = dev_upload(m, z); }
         if (ci == 2) { m->conv2_w = dst; m->conv2_b = b; } else { m->conv3_w = dst; m->conv3_b = b; }
     }
-    m->conv_out_w = take<bf16>(m, a + ".conv_out.weight", {dm, (int64_t)d.feat}, true);
+    {
+        const bf16* src = take<bf16>(m, a + ".conv_out.weight", {dm, (int64_t)d.feat}, true);
+        bf16* dst = dev_alloc<bf16>(m, (size_t)dm * d.feat);
+        permute_convout_kernel<<<1184, 256>>>(src, dst, (size_t)dm, (int)dsh, d.conv_h[3]);
+        ASRB_CUDA_CHECK(cudaGetLastError());
+        ASRB_CUDA_CHECK(cudaDeviceSynchronize());
+        drop_raw(m, a + ".conv_out.weight");
+        m->conv_out_w = dst;
+    }
     m->conv_out_b = opt_f32(m, a + ".conv_out.bias", {dm});
     m->enc.resize(c.encoder_layers);
     for (int i = 0; i < c.encoder_layers; ++i) {

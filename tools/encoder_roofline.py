@@ -11,7 +11,7 @@ clips = [synth.make_clip(i, 30.0) for i in range(B)]
 GFLOP_PER_CLIP = 270.7      # SURVEY.md section 8d (conv1 0.83 + conv2 99.53 + conv3 25.88 + conv_out 5.37 + 18 layers 135.26 + attn 2.49 + head 1.34)
 PREFILL_GFLOP = 356.7 + 18.8 + 0.31
 out = {}
-for planes in ("3", "2", "1"):
+for planes in os.environ.get("PLANES", "3,2,1").split(","):
     eng.set_option("planes", planes)
     for _ in range(2):
         r = eng.transcribe_ids(clips, max_new_tokens=2)

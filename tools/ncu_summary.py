@@ -18,7 +18,8 @@ def f(r, k):
 def scale(k, v):
     if v is None: return None
     u = units[col[k]]
-    m = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}
+    m = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0,
+         "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
     return v * m.get(u, 1.0)
 out = []
 for r in data:
