@@ -319,6 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // split-K second pass: sum the partial tiles in a fixed order, then the GEMM's own epilogue (bias / GELU / residual / split3)
+template <int MODE>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int S, int M, int N, GemmEpi E) {
     const int n8 = N / 8;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
         const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
         v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
     }
-    epi_store8<EPI_PLAIN>(E, N, m, n, v);
+    epi_store8<MODE>(E, N, m, n, v);
 }
 
 // ---- host: tensor maps ---------------------------------------------------------------------------
@@ -462,7 +463,7 @@ bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& Ein, cu
         // epilogue.  Deterministic; costs one extra fp32 round trip of the tile through L2.
         const int tiles = tiles_n * tiles_m, kblocks = A.K / BK;
         int splits = 1;
-        if (E.mode == EPI_PLAIN && E.splitk_ws && tiles <= 64 && N % 8 == 0 && (size_t)4 * A.M * N <= SPLITK_WS_FLOATS) {
+        if ((E.mode == EPI_PLAIN || E.mode == EPI_CONVOUT) && E.splitk_ws && tiles <= 64 && N % 8 == 0 && (size_t)4 * A.M * N <= SPLITK_WS_FLOATS) {
             for (int sp = 4; sp >= 2; --sp)
                 if (kblocks % sp == 0 && kblocks / sp >= 6 && tiles * sp <= 160) { splits = sp; break; }
         }
@@ -473,7 +474,8 @@ bool launch_gemm_tc(const GemmA& A, const bf16* W, int N, const GemmEpi& Ein, cu
             ASRB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<0, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             gemm_tc_kernel<0, EPI_PLAIN><<<std::min(tiles * splits, sms), NTHREADS, smem, st>>>(mapA, mapB, A.M, N, A.K, A.nplanes, tiles_m, tiles_n, splits, nacc, cg, P);
             const int work = A.M * (N / 8);
-            splitk_reduce_kernel<<<(work + 255) / 256, 256, 0, st>>>(E.splitk_ws, splits, A.M, N, E);
+            if (E.mode == EPI_PLAIN) splitk_reduce_kernel<EPI_PLAIN><<<(work + 255) / 256, 256, 0, st>>>(E.splitk_ws, splits, A.M, N, E);
+            else splitk_reduce_kernel<EPI_CONVOUT><<<(work + 255) / 256, 256, 0, st>>>(E.splitk_ws, splits, A.M, N, E);
             ASRB_CUDA_CHECK(cudaGetLastError());
             if (E.extra_launches) *E.extra_launches += 1;
             return true;

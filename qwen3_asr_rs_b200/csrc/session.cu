@@ -343,6 +343,7 @@ void session_encode(Session* s, int64_t* n_tokens_out) {
     {   // conv_out + positional embedding + valid-token gather -> x_enc [totT][d_model]
         GemmA A = plainA(s->feat, s->feat_ps, totC * tpc, d.feat, np);
         GemmEpi E; E.mode = EPI_CONVOUT; E.bias = m.conv_out_b; E.out_f32 = s->x_enc; E.ldo = c.d_model;
+        E.splitk_ws = s->splitk_ws; E.extra_launches = &s->launches;
         E.row_map = s->d_rowmap; E.pos = m.pos_emb; E.pos_period = tpc;
         launch_gemm(A, m.conv_out_w, c.d_model, E, s->gemm_impl, st);
     }

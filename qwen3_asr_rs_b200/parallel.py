@@ -47,7 +47,7 @@ class _DevView:
     """Zero-copy view of library-owned device memory for torch (``__cuda_array_interface__``)."""
 
     def __init__(self, ptr: int, shape, typestr: str = "<i4"):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), True),
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),   # torch rejects read-only views; IdsGather only reads
                                          "version": 3, "strides": None}
 
 
@@ -76,8 +76,9 @@ class IdsGather:
         n = min(batch, self.per)
         ids = torch.as_tensor(_DevView(ids_ptr, (batch, stride)), device=self.send.device)
         lens = torch.as_tensor(_DevView(lens_ptr, (batch,)), device=self.send.device)
-        self.send[:n, 0] = lens[:n].clamp(max=self.max_new)
-        self.send[:n, 1:] = ids[:n, : self.max_new]
+        w = min(stride, self.max_new)
+        self.send[:n, 0] = lens[:n].clamp(max=w)
+        self.send[:n, 1:1 + w] = ids[:n, :w]
         dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
         self.host.copy_(self.recv, non_blocking=False)
         res: List[List[int]] = []

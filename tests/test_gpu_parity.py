@@ -548,3 +548,24 @@ def test_transcribe_pcm_equals_host_ingest(tiny, tiny_engine):
     got = tiny_engine.transcribe_pcm([pcm24, pcm48], [24000, 48000], max_new_tokens=10).ids
     assert got == want
     assert got[0] == O.transcribe_ids(model, host[0], max_new_tokens=10).ids
+
+
+def test_ids_gather_reads_device_buffers(tiny_engine):
+    """parallel.IdsGather (bench.py's N > 1 path): the ids all_gather reads the session's own device buffers
+    (asrb_session_device_ids) -- single-rank NCCL group here, the 2-rank logic is covered on gloo in test_parallel.py."""
+    import torch
+    import torch.distributed as dist
+    from qwen3_asr_rs_b200 import parallel
+    own = not dist.is_initialized()
+    if own:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", world_size=1, rank=0)
+    try:
+        clips = [synth.make_clip(90 + i, 1.5 + 0.4 * i) for i in range(3)]
+        want = tiny_engine.transcribe_ids(clips, max_new_tokens=9).ids
+        g = parallel.IdsGather(1, len(clips), 9, torch.device("cuda", 0))
+        assert g(tiny_engine) == want
+        want2 = tiny_engine.transcribe_ids(clips[:2], max_new_tokens=5).ids       # smaller batch, shorter rows: no stale ids
+        assert g(tiny_engine)[:2] == want2
+    finally:
+        if own:
+            dist.destroy_process_group()
