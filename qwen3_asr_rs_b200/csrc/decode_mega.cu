@@ -102,8 +102,8 @@ __device__ __forceinline__ void produce(const Slice& s, const Ring& ring, uint32
 // (c * 32 + lane) * 8 .. +8 for every 256-element chunk c in registers.
 template <int K>
 __device__ __forceinline__ void load_xr(const float* xs, float (&xr)[K / 32], int lane) {
-#pragma unroll
     const int sw = ((lane >> 2) & 1) * 4;          // xs_swz for this lane's two 16-byte groups: swapped when bit 3 of k is set
+#pragma unroll
     for (int c = 0; c < K / 256; ++c) {
         const float4 a = *reinterpret_cast<const float4*>(xs + (c * 32 + lane) * 8 + sw);
         const float4 b = *reinterpret_cast<const float4*>(xs + (c * 32 + lane) * 8 + 4 - sw);
@@ -114,8 +114,8 @@ __device__ __forceinline__ void load_xr(const float* xs, float (&xr)[K / 32], in
 // same, with the RMSNorm applied on the fly: xr = (x * r) * w  (rounding order of layers.rs:48-54)
 template <int K>
 __device__ __forceinline__ void load_xr_norm(const float* xs, const float* wn, float r, float (&xr)[K / 32], int lane) {
-#pragma unroll
     const int sw = ((lane >> 2) & 1) * 4;          // both vectors are stored in the xs_swz layout
+#pragma unroll
     for (int c = 0; c < K / 256; ++c) {
         const int o = (c * 32 + lane) * 8;
         const float4 a = *reinterpret_cast<const float4*>(xs + o + sw), b = *reinterpret_cast<const float4*>(xs + o + 4 - sw);
@@ -181,7 +181,185 @@ __device__ __forceinline__ float row_dot_smem(const uint4* wrow, const float* xs
     return warp_sum(a0 + a1);
 }
 
+
+// four rows at once (K <= 1024, activations in registers): 8 independent FMA chains and ONE 6-shuffle transposed
+// reduction for the four rows instead of two 5-shuffle reductions of row pairs.  The sum of row j ends up in all 8 lanes
+// with (lane >> 3) == j.
+template <int K>
+__device__ __forceinline__ float row_dot4(const uint4* w0, const uint4* w1, const uint4* w2, const uint4* w3,
+                                          const float (&xr)[K / 32], int lane) {
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f, d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < K / 256; ++c) {
+        const uint4 wa = w0[c * 32 + lane], wb = w1[c * 32 + lane], wc = w2[c * 32 + lane], wd = w3[c * 32 + lane];
+#define ROW4_STEP(F, X0, X1)                                                                                          \
+        a0 = fmaf(bf16_lo(wa.F), X0, a0); a1 = fmaf(bf16_hi(wa.F), X1, a1);                                           \
+        b0 = fmaf(bf16_lo(wb.F), X0, b0); b1 = fmaf(bf16_hi(wb.F), X1, b1);                                           \
+        c0 = fmaf(bf16_lo(wc.F), X0, c0); c1 = fmaf(bf16_hi(wc.F), X1, c1);                                           \
+        d0 = fmaf(bf16_lo(wd.F), X0, d0); d1 = fmaf(bf16_hi(wd.F), X1, d1);
+        ROW4_STEP(x, xr[c * 8 + 0], xr[c * 8 + 1])
+        ROW4_STEP(y, xr[c * 8 + 2], xr[c * 8 + 3])
+        ROW4_STEP(z, xr[c * 8 + 4], xr[c * 8 + 5])
+        ROW4_STEP(w, xr[c * 8 + 6], xr[c * 8 + 7])
+#undef ROW4_STEP
+    }
+    const float ra = a0 + a1, rb = b0 + b1, rc = c0 + c1, rd = d0 + d1;
+    const bool h16 = lane & 16, h8 = lane & 8;
+    float k0 = (h16 ? rc : ra) + __shfl_xor_sync(0xffffffffu, h16 ? ra : rc, 16);      // rows {0,1} stay low, {2,3} high
+    float k1 = (h16 ? rd : rb) + __shfl_xor_sync(0xffffffffu, h16 ? rb : rd, 16);
+    float keep = (h8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, h8 ? k0 : k1, 8);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    return keep;
+}
+
+// transposed warp reduction of 8 per-lane partials: returns, in every lane, the warp total of value index (lane >> 2)
+__device__ __forceinline__ float warp_reduce8(const float (&a)[8], int lane) {
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    float k[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) k[i] = (h16 ? a[4 + i] : a[i]) + __shfl_xor_sync(0xffffffffu, h16 ? a[i] : a[4 + i], 16);
+    float m0 = (h8 ? k[2] : k[0]) + __shfl_xor_sync(0xffffffffu, h8 ? k[0] : k[2], 8);
+    float m1 = (h8 ? k[3] : k[1]) + __shfl_xor_sync(0xffffffffu, h8 ? k[1] : k[3], 8);
+    float v = (h4 ? m1 : m0) + __shfl_xor_sync(0xffffffffu, h4 ? m0 : m1, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
 enum { ME_STORE = 0, ME_RESID = 1, ME_SWIGLU = 2, ME_ARGMAX = 3 };
+
+// Residual GEMVs (o_proj, down_proj: a handful of rows per CTA, long K): all 8 warps split K of EVERY row instead of one
+// warp per row.  A thread owns the 16-byte weight groups tid, tid + 256, ... of each row (its 8 activations per group come
+// straight from xs), keeps one partial per row (8 independent FMA chains), the warp reduces its 8 partials with one
+// transposed reduction (9 shuffles), the 8 warp partials of a row are summed in a fixed order by one thread, which applies
+// the residual and publishes.  Rows are taken 8 at a time; a group spans two ring slots when a slot holds fewer than 8.
+// (The one-warp-per-row form left 1 of 8 warps idle and paid the load -> unpack -> FMA -> 5-shuffle latency chain once per
+// row with nothing to overlap it: 1.6 k / 1.9 k cycles per layer for 7 rows.)
+template <int K>
+__device__ __forceinline__ void consume_ksplit(const Slice& s, const Ring& ring, uint32_t& q, const float* xs, uint2* out,
+                                               uint32_t tag, float* xres, float* part) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NU = K / 8;                                  // 16-byte groups per row
+    constexpr int J = (NU + NCONS - 1) / NCONS;
+    uint32_t grp = 0;
+    for (int r = s.r0; r < s.r1;) {
+        const int rowsA = min(s.rpc, s.r1 - r);
+        const uint32_t slotA = q % ring.nslot;
+        mbar_wait(&ring.full[slotA], (q / ring.nslot) & 1);
+        const bool pair = s.rpc < 8 && r + rowsA < s.r1;
+        const int rowsB = pair ? min(s.rpc, s.r1 - r - rowsA) : 0;
+        const uint32_t slotB = (q + 1) % ring.nslot;
+        if (pair) mbar_wait(&ring.full[slotB], ((q + 1) / ring.nslot) & 1);
+        const uint4* baseA = reinterpret_cast<const uint4*>(ring.slots + (size_t)slotA * SLOT_BYTES);
+        const uint4* baseB = reinterpret_cast<const uint4*>(ring.slots + (size_t)slotB * SLOT_BYTES);
+        const int R = rowsA + rowsB;
+        for (int g0 = 0; g0 < R; g0 += 8, ++grp) {
+            const int ng = min(8, R - g0);
+            const uint4* rp[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int ri = g0 + (i < ng ? i : 0);              // rows past the group re-read row 0 (result unused)
+                rp[i] = ri < rowsA ? baseA + (size_t)ri * NU : baseB + (size_t)(ri - rowsA) * NU;
+            }
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int idx = tid + j * NCONS;
+                if (idx < NU) {
+                    const int sw = ((idx >> 2) & 1) * 4;            // xs_swz of the two 16-byte activation groups
+                    const float4 xa = *reinterpret_cast<const float4*>(xs + idx * 8 + sw);
+                    const float4 xb = *reinterpret_cast<const float4*>(xs + idx * 8 + 4 - sw);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint4 w = rp[i][idx];
+                        float t = acc[i];
+                        t = fmaf(bf16_lo(w.x), xa.x, t); t = fmaf(bf16_hi(w.x), xa.y, t);
+                        t = fmaf(bf16_lo(w.y), xa.z, t); t = fmaf(bf16_hi(w.y), xa.w, t);
+                        t = fmaf(bf16_lo(w.z), xb.x, t); t = fmaf(bf16_hi(w.z), xb.y, t);
+                        t = fmaf(bf16_lo(w.w), xb.z, t); t = fmaf(bf16_hi(w.w), xb.w, t);
+                        acc[i] = t;
+                    }
+                }
+            }
+            const float v = warp_reduce8(acc, lane);
+            if (g0 + 8 >= R) {                                      // last group of these slots: every weight has been consumed
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&ring.empty[slotA]); if (pair) mbar_arrive(&ring.empty[slotB]); }
+            }
+            float* pb = part + (grp & 1) * 64;
+            if ((lane & 3) == 0) pb[warp * 8 + (lane >> 2)] = v;
+            cons_sync();                                            // (also: every read of xs by this group is done)
+            if (tid < ng) {
+                float t = pb[tid];
+#pragma unroll
+                for (int w8 = 1; w8 < NCONS_WARPS; ++w8) t += pb[w8 * 8 + tid];
+                const int row = r + g0 + tid;
+                const float nv = xres[row - s.r0] + t; xres[row - s.r0] = nv;
+                ll_store(out + row, nv, tag);
+            }
+        }
+        r += R; q += pair ? 2 : 1;
+    }
+}
+
+// K <= 1024 GEMVs (qkv, gate/up, lm_head of the 0.6B dims): four rows per warp and turn, two ring slots (32 rows) per turn.
+template <int K, int EPI>
+__device__ __forceinline__ void consume_quad(const Slice& s, const Ring& ring, uint32_t& q, const float* xs, uint2* out,
+                                             uint32_t tag, float& best_v, int& best_i,
+                                             const float* norm_w, float norm_r, long long* fine) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int fi = 0;
+#define CF() do { if (fine && threadIdx.x == 0 && fi < 24) fine[fi++] = clock64(); } while (0)
+    CF();
+    constexpr int NU = K / 8;
+    float xr[K / 32];
+    if (norm_w) load_xr_norm<K>(xs, norm_w, norm_r, xr, lane);
+    else load_xr<K>(xs, xr, lane);
+    cons_sync();                                   // every warp holds its copy: xs may be overwritten from here on
+    CF();
+    const int j = lane >> 3;                       // row of the quad whose total this lane holds after row_dot4
+    for (int r = s.r0; r < s.r1;) {
+        const int rowsA = min(s.rpc, s.r1 - r);
+        const uint32_t slotA = q % ring.nslot;
+        mbar_wait(&ring.full[slotA], (q / ring.nslot) & 1);
+        const bool pair = s.rpc < 32 && r + rowsA < s.r1;
+        const int rowsB = pair ? min(s.rpc, s.r1 - r - rowsA) : 0;
+        const uint32_t slotB = (q + 1) % ring.nslot;
+        if (pair) mbar_wait(&ring.full[slotB], ((q + 1) / ring.nslot) & 1);
+        CF();
+        const uint4* baseA = reinterpret_cast<const uint4*>(ring.slots + (size_t)slotA * SLOT_BYTES);
+        const uint4* baseB = reinterpret_cast<const uint4*>(ring.slots + (size_t)slotB * SLOT_BYTES);
+        const int R = rowsA + rowsB;
+        for (int i0 = 4 * warp; i0 < R; i0 += 4 * NCONS_WARPS) {
+            const int nv = min(4, R - i0);
+            const uint4* rp[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ri = i0 + (i < nv ? i : 0);
+                rp[i] = ri < rowsA ? baseA + (size_t)ri * NU : baseB + (size_t)(ri - rowsA) * NU;
+            }
+            const float v = row_dot4<K>(rp[0], rp[1], rp[2], rp[3], xr, lane);
+            const int row = r + i0 + j;
+            if (EPI == ME_SWIGLU) {                // rows (gate, up, gate, up): lanes 0 / 16 hold a gate, lanes 8 / 24 its up row
+                const float up = __shfl_xor_sync(0xffffffffu, v, 8);
+                if ((lane & 15) == 0 && j < nv) ll_store(out + (row >> 1), silu(v) * up, tag);
+            } else if (EPI == ME_STORE) {
+                if ((lane & 7) == 0 && j < nv) ll_store(out + row, v, tag);
+            } else {                               // ME_ARGMAX: rows arrive in increasing order per lane, strict > keeps the first maximum
+                if ((lane & 7) == 0 && j < nv && v > best_v) { best_v = v; best_i = row; }
+            }
+        }
+        CF();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&ring.empty[slotA]); if (pair) mbar_arrive(&ring.empty[slotB]); }
+        r += R; q += pair ? 2 : 1;
+    }
+    CF();
+#undef CF
+}
 
 // consumer: process all chunks of a slice.  `xs` holds the (already normalised) activation vector.
 // Results are published as tagged words to `out` (ME_STORE / ME_SWIGLU), added to the CTA-local
@@ -189,7 +367,10 @@ enum { ME_STORE = 0, ME_RESID = 1, ME_SWIGLU = 2, ME_ARGMAX = 3 };
 template <int K, int EPI>
 __device__ __forceinline__ void consume(const Slice& s, const Ring& ring, uint32_t& q, const float* xs, uint2* out,
                                         uint32_t tag, float* xres, float& best_v, int& best_i,
-                                        const float* norm_w = nullptr, float norm_r = 1.f, long long* fine = nullptr) {
+                                        const float* norm_w = nullptr, float norm_r = 1.f, long long* fine = nullptr,
+                                        float* part = nullptr) {
+    if constexpr (EPI == ME_RESID) { consume_ksplit<K>(s, ring, q, xs, out, tag, xres, part); return; }
+    else if constexpr (K <= 1024) { consume_quad<K, EPI>(s, ring, q, xs, out, tag, best_v, best_i, norm_w, norm_r, fine); return; }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int fi = 0;
 #define CF() do { if (fine && threadIdx.x == 0 && fi < 24) fine[fi++] = clock64(); } while (0)
@@ -337,6 +518,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     uint64_t* p_full = kv_empty + 1; uint64_t* p_empty = p_full + 2;   // [2] each
     float* red = reinterpret_cast<float*>(bars + 2 * NSLOT_MAX + 6);      // [64]
     int* ired = reinterpret_cast<int*>(red + 64);                      // [64]
+    float* part = reinterpret_cast<float*>(ired + 64);                 // [2][8 warps][8 rows] K-split partials (consume_ksplit)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_producer = warp == NCONS_WARPS;
 
@@ -700,7 +882,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
         MEGA_FINE(33);
         MEGA_GT(2);
         cons_sync();
-        consume<QD, ME_RESID>(sl_o, ring, q, xs, p.x_ll, tl | PH_XO, xres, best_v, best_i);
+        consume<QD, ME_RESID>(sl_o, ring, q, xs, p.x_ll, tl | PH_XO, xres, best_v, best_i, nullptr, 1.f, nullptr, part);
         MEGA_FINE(34);
         MEGA_MARK();
         // ---- phase 4: RMSNorm + gate/up GEMV + SiLU*mul ----
@@ -718,7 +900,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
         MEGA_FINE(16); MEGA_FINE(17);
         ll_gather(p.act_ll, I, tl | PH_ACT, xs); MEGA_FINE(18);
         cons_sync();
-        consume<I, ME_RESID>(sl_dn, ring, q, xs, p.x_ll, tl | PH_XD, xres, best_v, best_i);
+        consume<I, ME_RESID>(sl_dn, ring, q, xs, p.x_ll, tl | PH_XD, xres, best_v, best_i, nullptr, 1.f, nullptr, part);
         MEGA_FINE(19);
         MEGA_FINE(20);
         MEGA_MARK();
@@ -735,9 +917,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
     consume<H, ME_ARGMAX>(make_slice(p.lm_head, p.V, H, 1), ring, q, xs, nullptr, 0u, xres, best_v, best_i,
                           pbuf + (p.L & 1) * PARAM_FLOATS, nrf);
     MEGA_MARK();
-    // candidates live in lanes 0 and 16 of every warp (row 0 / row 1 of a turn): merge them, lane 0 publishes the warp's best
-    {
-        const float ov = __shfl_xor_sync(0xffffffffu, best_v, 16); const int oi = __shfl_xor_sync(0xffffffffu, best_i, 16);
+    // candidates live in lanes 0, 8, 16, 24 of every warp (the four rows of a turn; lanes 0 / 16 in the two-row form):
+    // merge them, lane 0 publishes the warp's best
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best_v, o); const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
         if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
     }
     cons_sync();
@@ -800,7 +984,7 @@ static int mega_xs_floats(int I) { return std::max(I, mega::XS_MIN) + 64; }
 static size_t mega_smem_bytes(int H, int I, int nslot) {
     return (size_t)nslot * mega::SLOT_BYTES + 2 * mega::KV_TILE_BYTES +
            (mega_xs_floats(I) + mega::XRES_MAX + 2 * (2 * H + 2 * mega::HD) + 128) * 4 + mega::MAX_LAYERS * sizeof(DecLayerW) +
-           (2 * mega::NSLOT_MAX + 6) * 8 + 64 * 4 + 64 * 4 + 64;
+           (2 * mega::NSLOT_MAX + 6) * 8 + 64 * 4 + 64 * 4 + 128 * 4 + 64;
 }
 // instantiations: (hidden, q_dim, intermediate) -> ring depth
 static int mega_nslot(const asrb_dims& c) { return c.hidden_size > 1024 ? 3 : 4; }
