@@ -5,8 +5,6 @@ mkdir -p gpurun_out
 echo "=== pytest gpu (all)"; timeout 2400 python -m pytest tests/ -q -m gpu --timeout 1200 > gpurun_out/pytest_gpu.log 2>&1; echo "exit $?"; tail -6 gpurun_out/pytest_gpu.log
 cp gpurun_out/parity_report.json gpurun_out/parity_all.json 2>/dev/null
 echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-echo "=== bench --impl reference"; /usr/bin/time -v timeout 900 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "exit $?"; cat gpurun_out/bench_ref.json; grep "Elapsed" gpurun_out/bench_ref.err
-echo "=== bench (default flags)"; /usr/bin/time -v timeout 1200 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cat gpurun_out/bench.json; grep "Elapsed" gpurun_out/bench.err; tail -3 gpurun_out/bench.err
 echo "=== decode step roofline at batch 1 / 8 / 16"; timeout 900 python tools/batch_decode_roofline.py 1 8 16 > gpurun_out/batch_decode.json 2> gpurun_out/batch_decode.err; echo "exit $?"; python - <<'PY'
 import json
 for l in open('gpurun_out/batch_decode.json'):
