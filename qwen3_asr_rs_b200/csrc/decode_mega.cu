@@ -47,14 +47,18 @@ struct Params {
     // tagged exchange buffers ({value, tag} words)
     uint2* qkv_ll; uint2* part_ll; uint2* attn_ll; uint2* x_ll; uint2* act_ll;
     long long* dbg;              // optional timeline [2][DBG_SLOTS] of clock64 (CTA 0 and CTA G-1), else null
+    int pf_ahead;                // L2 prefetch distance in ring chunks (0 = off)
 };
 
-// The shared-memory ring only buffers ~2.7 us of the weight stream (120 KB at this SM's 44 GB/s share of
-// HBM) while the consumers' dependency stalls last tens of us per layer.  So the producer also runs an
-// L2 prefetch cursor PF_AHEAD chunks (~1.5 layers, ~57 MB chip-wide of the 126 MB L2) ahead of the ring:
-// HBM streams continuously into L2, and the ring refills from L2 at low latency.
-static constexpr int PF_AHEAD = 0;    // measured: distances 16 / 4 / 0 give the same step time, but 16 costs +31 % DRAM reads
-                                      // (prefetched lines evicted before use; ncu 1.70 GB vs 1.30 GB algorithmic) -> off
+// The shared-memory ring only buffers ~2.7 us of the weight stream (120 KB at this SM's 44 GB/s share of HBM), and a ring
+// slot can only be refilled once its rows have been consumed: the refill of the slots a phase has just released must land
+// before the phase after next needs them.  With the refill coming from DRAM (~2 us) that was hidden behind the slow
+// all-gathers; once the gathers re-read only their missing words (ll_gather, mega_common.cuh) the GEMV turns started to wait
+// ~600 cycles for their slots.  So the producer also runs an L2 prefetch cursor `pf_ahead` ring chunks ahead of the ring
+// (ASRB_MEGA_PF overrides): the refill then comes from L2.  Measured with the selective re-poll (trip 34, us per step):
+// distance 0: 452, 2: 432, 4: 432, 8: 436, 16: 512 (prefetched lines evicted before use: +31 % DRAM reads in round 1).
+static constexpr int PF_AHEAD = 2;
+
 template <int H, int QD, int I>
 struct ChunkCursor {
     int l, ph, r; Slice s; bool done;
@@ -94,7 +98,7 @@ __device__ __forceinline__ void produce(const Slice& s, const Ring& ring, uint32
         mbar_expect_tx(&ring.full[slot], bytes);
         bulk_g2s(ring.slots + (size_t)slot * SLOT_BYTES, s.W + (size_t)r * s.K, bytes, &ring.full[slot]);
         const bf16* psrc; uint32_t pbytes;
-        if (PF_AHEAD > 0 && pf.next(p, psrc, pbytes)) l2_prefetch(psrc, pbytes);
+        if (p.pf_ahead > 0 && pf.next(p, psrc, pbytes)) l2_prefetch(psrc, pbytes);
     }
 }
 
@@ -555,7 +559,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
             pf.init(p, ltab);
             {   // start the HBM stream immediately: the first PF_AHEAD chunks go to L2 now
                 const bf16* psrc; uint32_t pbytes;
-                for (int i = 0; i < PF_AHEAD; ++i) if (pf.next(p, psrc, pbytes)) l2_prefetch(psrc, pbytes);
+                for (int i = 0; i < p.pf_ahead; ++i) if (pf.next(p, psrc, pbytes)) l2_prefetch(psrc, pbytes);
             }
             const size_t kv_row = ((size_t)att_g * p.max_ctx + att_j0) * HD;
             if (n_old > 0) {   // K/V tiles of the first two layers
@@ -603,7 +607,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const Params p
                 ChunkCursor<H, QD, I> nx;
                 nx.init(p, ltab);
                 const bf16* psrc; uint32_t pbytes;
-                for (int i = 0; i < PF_AHEAD; ++i) if (nx.next(p, psrc, pbytes)) l2_prefetch(psrc, pbytes);
+                for (int i = 0; i < p.pf_ahead; ++i) if (nx.next(p, psrc, pbytes)) l2_prefetch(psrc, pbytes);
             }
         }
         return;
@@ -1058,6 +1062,8 @@ void launch_decode_step_mega(const Model& m, const DecodeBufs& b, int B, float* 
         p.act_ll = w; w += c.intermediate_size;
         p.dbg = mb.dbg;
         g_last_dbg = mb.dbg;
+        static const int pf_env = [] { const char* e = getenv("ASRB_MEGA_PF"); return e ? atoi(e) : mega::PF_AHEAD; }();
+        p.pf_ahead = pf_env;
         // tags must stay monotonic for red.max publication: long before the 24-bit epoch wraps, wipe the exchange buffers
         if (mb.steps_issued && ++*mb.steps_issued >= 0xFFFF00u) {
             ASRB_CUDA_CHECK(cudaMemsetAsync(mb.part, 0, mb.part_bytes, st));
